@@ -1,0 +1,155 @@
+/*
+ * msdfgen_b200.h — C ABI of the B200-native MSDF generator (libmsdfgen_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of Chlumsky/msdfgen: per-pixel signed-distance-field generation plus
+ * the MSDF error-correction pass.  The reference exposes that path as C++ free functions (there is no FFI in the
+ * reference; substitution is at link time), so each entry point below names the reference interface it replaces:
+ *
+ *   b200msdf_generate            <-> generateSDF / generatePSDF / generateMSDF / generateMTSDF
+ *                                    (/root/reference/msdfgen.h:47-56, core/msdfgen.cpp:78-106)
+ *   b200msdf_generate_batch      <-> the loop a caller (e.g. msdf-atlas-gen) runs over those four for a font atlas
+ *   b200msdf_error_correction    <-> msdfErrorCorrection            (core/msdf-error-correction.h:15-18, .cpp:61-72)
+ *   b200msdf_fast_error_correction <-> msdfFastDistanceErrorCorrection / msdfFastEdgeErrorCorrection (.h:21-34)
+ *   b200msdf_batch_*             <-> same path with inputs/outputs resident in HBM (no reference counterpart)
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  All functions return 0 on success and a negative
+ * b200msdf_status on failure; b200msdf_last_error() gives the message.  There is NO CPU fallback: without a CUDA
+ * device every compute entry point fails with B200MSDF_ERR_CUDA.
+ *
+ * Semantics match the reference bit-for-bit in intent: fp64 distance arithmetic, fp32 texels, identical treatment of
+ * Y orientation (output.reorient(shape.getYAxisOrientation()), core/msdfgen.cpp:55), negative row strides, empty
+ * shapes (all texels -inf) and empty contours (skipped, core/ShapeDistanceFinder.hpp:19).
+ */
+#ifndef MSDFGEN_B200_H
+#define MSDFGEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MSDF_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    B200MSDF_OK = 0,
+    B200MSDF_ERR_ARG = -1,     /* invalid argument */
+    B200MSDF_ERR_CUDA = -2,    /* CUDA runtime / no device */
+    B200MSDF_ERR_ALLOC = -3    /* host or device allocation failed */
+} b200msdf_status;
+
+/* Which generator: selects the edge selector (core/msdfgen.cpp:78-106) and the channel count N = 1,1,3,4. */
+typedef enum {
+    B200MSDF_SDF = 1,    /* TrueDistanceSelector          -> generateSDF   */
+    B200MSDF_PSDF = 2,   /* PerpendicularDistanceSelector -> generatePSDF  */
+    B200MSDF_MSDF = 3,   /* MultiDistanceSelector         -> generateMSDF  (+ error correction) */
+    B200MSDF_MTSDF = 4   /* MultiAndTrueDistanceSelector  -> generateMTSDF (+ error correction) */
+} b200msdf_mode;
+
+/* ErrorCorrectionConfig::Mode / ::DistanceCheckMode, core/generator-config.h:19-36 (same numeric values). */
+enum { B200MSDF_EC_DISABLED = 0, B200MSDF_EC_INDISCRIMINATE = 1, B200MSDF_EC_EDGE_PRIORITY = 2, B200MSDF_EC_EDGE_ONLY = 3 };
+enum { B200MSDF_DCM_DO_NOT_CHECK = 0, B200MSDF_DCM_CHECK_AT_EDGE = 1, B200MSDF_DCM_ALWAYS_CHECK = 2 };
+
+/*
+ * A batch of shapes, flattened from Shape -> Contour -> EdgeHolder -> EdgeSegment
+ * (core/Shape.h:15-58, Contour.h:10-32, edge-segments.h:15-144).  One glyph = one Shape.
+ */
+typedef struct {
+    int32_t n_glyphs;
+    int32_t n_contours;                      /* total over all glyphs */
+    int32_t n_segments;                      /* total over all glyphs */
+    const uint32_t *glyph_contour_begin;     /* [n_glyphs+1]   contour range of glyph g (Shape::contours)           */
+    const uint32_t *contour_segment_begin;   /* [n_contours+1] segment range of contour c, in Contour::edges order  */
+    const double *points;                    /* [n_segments][8] control points p0..p3 (x,y); unused slots ignored   */
+    const uint8_t *orders;                   /* [n_segments]   EdgeSegment::type(): 1 linear, 2 quadratic, 3 cubic  */
+    const uint8_t *colors;                   /* [n_segments]   EdgeColor bitmask (EdgeColor.h); NULL = all WHITE    */
+    const uint8_t *y_downward;               /* [n_glyphs]     Shape::inverseYAxis; NULL = all Y_UPWARD             */
+} b200msdf_shapes;
+
+/* SDFTransformation = Projection{scale, translate} + DistanceMapping{scale, translate} (core/Projection.h:31-33,
+ * core/DistanceMapping.h:28-30).  For DistanceMapping(Range r): dm_scale = 1/(r.upper-r.lower), dm_translate = -r.lower. */
+typedef struct {
+    double scale_x, scale_y;
+    double translate_x, translate_y;
+    double dm_scale, dm_translate;
+} b200msdf_transform;
+
+/* BitmapSection<float, N> (core/BitmapRef.hpp:74-111): host memory, row_stride in floats (may be negative). */
+typedef struct {
+    float *pixels;
+    int32_t width, height;
+    int32_t row_stride;
+    int32_t y_downward;                      /* BitmapSection::yOrientation == Y_DOWNWARD */
+} b200msdf_bitmap;
+
+/* MSDFGeneratorConfig = GeneratorConfig{overlapSupport} + ErrorCorrectionConfig (core/generator-config.h:13-64). */
+typedef struct {
+    int32_t overlap_support;                 /* default 1 */
+    int32_t ec_mode;                         /* default B200MSDF_EC_EDGE_PRIORITY */
+    int32_t ec_distance_check_mode;          /* default B200MSDF_DCM_CHECK_AT_EDGE */
+    double min_deviation_ratio;              /* default 1.11111111111111111 */
+    double min_improve_ratio;                /* default 1.11111111111111111 */
+    uint8_t *ec_buffer;                      /* ErrorCorrectionConfig::buffer: optional, >= width*height bytes; single-shape calls
+                                                only; receives the stencil like the reference's does */
+} b200msdf_config;
+
+typedef struct b200msdf_ctx b200msdf_ctx;       /* one per (thread, GPU): stream, pooled device + pinned buffers */
+typedef struct b200msdf_batch b200msdf_batch;   /* a shape batch resident in HBM with its output buffers */
+
+/* ---- lifecycle ---------------------------------------------------------------------------------------------------- */
+int b200msdf_version(void);
+const char *b200msdf_last_error(void);                       /* thread-local message of the last failing call */
+void b200msdf_default_config(b200msdf_config *cfg);          /* MSDFGeneratorConfig() defaults */
+int b200msdf_create(int device, b200msdf_ctx **ctx);         /* device = CUDA ordinal */
+void b200msdf_destroy(b200msdf_ctx *ctx);
+int b200msdf_set_stream(b200msdf_ctx *ctx, void *cuda_stream);   /* run on the caller's cudaStream_t (NULL = own stream) */
+int b200msdf_synchronize(b200msdf_ctx *ctx);
+/* Number of kernels this context has launched so far (for bench.py's gpu_launches). */
+uint64_t b200msdf_launch_count(const b200msdf_ctx *ctx);
+/* Pinned host memory for callers that want DMA-speed transfers. */
+int b200msdf_host_alloc(void **ptr, size_t bytes);
+void b200msdf_host_free(void *ptr);
+
+/* ---- host-buffer entry points (synchronous; results are in host memory on return) ----------------------------------- */
+
+/* generate{SDF,PSDF,MSDF,MTSDF}(output, shape, transformation, config): shapes->n_glyphs must be 1. */
+int b200msdf_generate(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shape, const b200msdf_transform *transformation,
+                      const b200msdf_bitmap *output, const b200msdf_config *config);
+
+/* One generate* call per glyph of the batch. transformations: [1] shared or [n_glyphs] (transform_per_glyph != 0);
+ * outputs: [n_glyphs] BitmapSections (any sizes/strides/orientations). config->ec_buffer is ignored. */
+int b200msdf_generate_batch(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
+                            int transform_per_glyph, const b200msdf_bitmap *outputs, const b200msdf_config *config);
+
+/* msdfErrorCorrection(sdf, shape, transformation, config) on existing N-channel fields (N = 3 or 4), in place. */
+int b200msdf_error_correction(b200msdf_ctx *ctx, int channels, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
+                              int transform_per_glyph, const b200msdf_bitmap *sdfs, const b200msdf_config *config);
+
+/* msdfFastDistanceErrorCorrection (edge == 0) / msdfFastEdgeErrorCorrection (edge != 0): shapeless variants, in place. */
+int b200msdf_fast_error_correction(b200msdf_ctx *ctx, int channels, int edge, const b200msdf_transform *transformation,
+                                   const b200msdf_bitmap *sdf, double min_deviation_ratio);
+
+/* ---- HBM-resident batches (asynchronous on the context's stream) ---------------------------------------------------- */
+
+/* Uploads shapes + per-glyph geometry and allocates outputs. dims: [2] shared (w,h) or [2*n_glyphs] (dims_per_glyph != 0).
+ * out_y_downward: [n_glyphs] or NULL.  Output layout: glyph g is a packed [h][w][N] float block at
+ * b200msdf_batch_glyph_offset(batch, g) floats from the start of the output buffer (offsets are multiples of 4 floats). */
+int b200msdf_batch_upload(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
+                          int transform_per_glyph, const int32_t *dims, int dims_per_glyph, const uint8_t *out_y_downward,
+                          b200msdf_batch **batch);
+/* Enqueues the whole path (contour windings -> distance field -> error correction) for the batch. */
+int b200msdf_batch_launch(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200msdf_config *config);
+float *b200msdf_batch_device_output(const b200msdf_batch *batch);      /* device pointer, valid until batch_free */
+uint8_t *b200msdf_batch_device_stencil(const b200msdf_batch *batch);   /* device pointer to per-texel EC flags (1 byte/texel) */
+size_t b200msdf_batch_output_floats(const b200msdf_batch *batch);      /* total floats incl. alignment padding */
+size_t b200msdf_batch_glyph_offset(const b200msdf_batch *batch, int glyph);
+/* D2H of the whole output buffer into host_dst (>= output_floats*4 bytes) and stream sync. */
+int b200msdf_batch_download(b200msdf_ctx *ctx, b200msdf_batch *batch, float *host_dst);
+void b200msdf_batch_free(b200msdf_ctx *ctx, b200msdf_batch *batch);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,288 @@
+"""Python mirror of the reference's generator interface, bound to the C ABI (include/msdfgen_b200.h) with ctypes.
+
+The names follow msdfgen.h (/root/reference/msdfgen.h:47-56): ``generateSDF / generatePSDF / generateMSDF / generateMTSDF``
+take a shape, an SDFTransformation and a generator config and fill a float bitmap; ``msdfErrorCorrection`` and the
+``msdfFast*ErrorCorrection`` variants mirror core/msdf-error-correction.h.  Batched variants take a FlatShapes atlas.
+All compute happens in the CUDA library; this module only marshals numpy arrays across the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .flat import FlatShapes
+
+SDF, PSDF, MSDF, MTSDF = 1, 2, 3, 4
+CHANNELS = {SDF: 1, PSDF: 1, MSDF: 3, MTSDF: 4}
+EC_DISABLED, EC_INDISCRIMINATE, EC_EDGE_PRIORITY, EC_EDGE_ONLY = 0, 1, 2, 3
+DCM_DO_NOT_CHECK, DCM_CHECK_AT_EDGE, DCM_ALWAYS_CHECK = 0, 1, 2
+DEFAULT_RATIO = 1.11111111111111111
+
+
+@dataclass
+class ErrorCorrectionConfig:
+    """core/generator-config.h:13-46"""
+    mode: int = EC_EDGE_PRIORITY
+    distanceCheckMode: int = DCM_CHECK_AT_EDGE
+    minDeviationRatio: float = DEFAULT_RATIO
+    minImproveRatio: float = DEFAULT_RATIO
+
+
+@dataclass
+class MSDFGeneratorConfig:
+    """core/generator-config.h:49-64 (GeneratorConfig + errorCorrection)"""
+    overlapSupport: bool = True
+    errorCorrection: ErrorCorrectionConfig = None
+
+    def __post_init__(self):
+        if self.errorCorrection is None:
+            self.errorCorrection = ErrorCorrectionConfig()
+
+    def c(self, ec_buffer=None):
+        cfg = _lib.Config(int(self.overlapSupport), self.errorCorrection.mode, self.errorCorrection.distanceCheckMode,
+                          self.errorCorrection.minDeviationRatio, self.errorCorrection.minImproveRatio, None)
+        if ec_buffer is not None:
+            cfg.ec_buffer = ec_buffer.ctypes.data_as(C.POINTER(C.c_uint8))
+        return cfg
+
+
+GeneratorConfig = MSDFGeneratorConfig
+
+
+@dataclass
+class SDFTransformation:
+    """Projection(scale, translate) + DistanceMapping(Range(lower, upper)) — core/SDFTransformation.h, DistanceMapping.cpp:13."""
+    scale: tuple
+    translate: tuple
+    range_lower: float
+    range_upper: float
+
+    @staticmethod
+    def from_array(a):
+        a = np.asarray(a, dtype=np.float64)
+        return SDFTransformation((a[0], a[1]), (a[2], a[3]), a[4], a[5])
+
+    def c(self):
+        lower, upper = np.float64(self.range_lower), np.float64(self.range_upper)
+        return _lib.Transform(self.scale[0], self.scale[1], self.translate[0], self.translate[1], float(np.float64(1.0) / (upper - lower)), float(-lower))
+
+
+def _transforms(xf):
+    """Accepts SDFTransformation | array[6] | array[n,6] (sx, sy, tx, ty, range_lower, range_upper) -> (ctypes array, per_glyph)."""
+    if isinstance(xf, SDFTransformation):
+        return (_lib.Transform * 1)(xf.c()), 0
+    a = np.asarray(xf, dtype=np.float64).reshape(-1, 6)
+    arr = (_lib.Transform * len(a))()
+    for i, r in enumerate(a):
+        arr[i] = SDFTransformation.from_array(r).c()
+    return arr, (1 if len(a) > 1 else 0)
+
+
+def _shapes_struct(s: FlatShapes):
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    return _lib.Shapes(s.n_glyphs, s.n_contours, s.n_segments, p(s.gbegin, C.c_uint32), p(s.cbegin, C.c_uint32), p(s.points, C.c_double),
+                       p(s.orders, C.c_uint8), p(s.colors, C.c_uint8), p(s.ydown, C.c_uint8))
+
+
+def _bitmap(a, ydown=False):
+    h, w, n = a.shape
+    assert a.dtype == np.float32 and a.strides[2] == 4 and a.strides[1] == 4 * n and a.strides[0] % 4 == 0
+    return _lib.Bitmap(a.ctypes.data_as(C.POINTER(C.c_float)), w, h, a.strides[0] // 4, int(ydown))
+
+
+class Context:
+    """One per thread and GPU (b200msdf_ctx): owns the stream and the pooled device / pinned buffers."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        self.h = C.c_void_p()
+        _lib.check(self.lib.b200msdf_create(device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.lib.b200msdf_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        _lib.check(self.lib.b200msdf_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        _lib.check(self.lib.b200msdf_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.b200msdf_launch_count(self.h))
+
+    def pinned(self, shape, dtype):
+        """numpy array backed by pinned host memory from b200msdf_host_alloc (kept alive by the returned array's base)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = C.c_void_p()
+        _lib.check(self.lib.b200msdf_host_alloc(C.byref(ptr), max(n, 1)))
+        buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
+        lib = self.lib
+
+        class _Owner:
+            def __init__(self):
+                self.ptr, self.buf = ptr, buf
+
+            def __del__(self):
+                lib.b200msdf_host_free(self.ptr)
+        owner = _Owner()
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        arr._b200_owner = owner if False else None  # numpy arrays cannot take attributes; keep owner in registry instead
+        _PINNED_OWNERS[id(buf)] = owner
+        return arr
+
+    # ---- reference-shaped single-shape calls ----------------------------------------------------------------------
+    def generate(self, mode, output, shape: FlatShapes, transformation, config: MSDFGeneratorConfig = None, out_ydown=False,
+                 ec_buffer=None):
+        config = config or MSDFGeneratorConfig()
+        assert shape.n_glyphs == 1 and output.shape[2] == CHANNELS[mode]
+        xf, _ = _transforms(transformation)
+        bm = _bitmap(output, out_ydown)
+        s = _shapes_struct(shape)
+        cfg = config.c(ec_buffer)
+        _lib.check(self.lib.b200msdf_generate(self.h, mode, C.byref(s), xf, C.byref(bm), C.byref(cfg)))
+        return output
+
+    def generate_batch(self, mode, outputs, shapes: FlatShapes, transformations, config: MSDFGeneratorConfig = None, out_ydown=None):
+        """outputs: float32[nGlyphs,h,w,N] (one block) or a list of per-glyph float32[h,w,N] arrays."""
+        config = config or MSDFGeneratorConfig()
+        xf, per = _transforms(transformations)
+        n = shapes.n_glyphs
+        bms = (_lib.Bitmap * max(n, 1))()
+        for g in range(n):
+            bms[g] = _bitmap(outputs[g], bool(out_ydown[g]) if out_ydown is not None else False)
+        s = _shapes_struct(shapes)
+        cfg = config.c()
+        _lib.check(self.lib.b200msdf_generate_batch(self.h, mode, C.byref(s), xf, per, bms, C.byref(cfg)))
+        return outputs
+
+    def error_correction(self, sdfs, shapes: FlatShapes, transformations, config: MSDFGeneratorConfig = None, sdf_ydown=None, ec_buffer=None):
+        config = config or MSDFGeneratorConfig()
+        xf, per = _transforms(transformations)
+        n = shapes.n_glyphs
+        bms = (_lib.Bitmap * max(n, 1))()
+        for g in range(n):
+            bms[g] = _bitmap(sdfs[g], bool(sdf_ydown[g]) if sdf_ydown is not None else False)
+        s = _shapes_struct(shapes)
+        cfg = config.c(ec_buffer)
+        _lib.check(self.lib.b200msdf_error_correction(self.h, sdfs[0].shape[2], C.byref(s), xf, per, bms, C.byref(cfg)))
+        return sdfs
+
+    def fast_error_correction(self, sdf, transformation, edge: bool, min_deviation_ratio=DEFAULT_RATIO):
+        xf, _ = _transforms(transformation)
+        bm = _bitmap(sdf)
+        _lib.check(self.lib.b200msdf_fast_error_correction(self.h, sdf.shape[2], int(edge), xf, C.byref(bm), min_deviation_ratio))
+        return sdf
+
+    # ---- HBM-resident batches --------------------------------------------------------------------------------------
+    def upload(self, mode, shapes: FlatShapes, transformations, dims, out_ydown=None):
+        return Batch(self, mode, shapes, transformations, dims, out_ydown)
+
+
+_PINNED_OWNERS = {}
+
+
+class Batch:
+    """b200msdf_batch: shapes + geometry resident in HBM, with device output buffers."""
+
+    def __init__(self, ctx: Context, mode, shapes: FlatShapes, transformations, dims, out_ydown=None):
+        self.ctx, self.mode, self.n = ctx, mode, shapes.n_glyphs
+        xf, per = _transforms(transformations)
+        d = np.ascontiguousarray(dims, dtype=np.int32).reshape(-1, 2)
+        self.dims = d
+        yd = np.ascontiguousarray(out_ydown, dtype=np.uint8) if out_ydown is not None else None
+        s = _shapes_struct(shapes)
+        self.h = C.c_void_p()
+        _lib.check(ctx.lib.b200msdf_batch_upload(ctx.h, mode, C.byref(s), xf, per, d.ctypes.data_as(C.POINTER(C.c_int32)), int(len(d) > 1),
+                                                 yd.ctypes.data_as(C.POINTER(C.c_uint8)) if yd is not None else None, C.byref(self.h)))
+
+    def launch(self, config: MSDFGeneratorConfig = None):
+        cfg = (config or MSDFGeneratorConfig()).c()
+        _lib.check(self.ctx.lib.b200msdf_batch_launch(self.ctx.h, self.h, C.byref(cfg)))
+
+    @property
+    def output_floats(self):
+        return int(self.ctx.lib.b200msdf_batch_output_floats(self.h))
+
+    @property
+    def device_output(self):
+        return self.ctx.lib.b200msdf_batch_device_output(self.h)
+
+    def glyph_offset(self, g):
+        return int(self.ctx.lib.b200msdf_batch_glyph_offset(self.h, g))
+
+    def download(self, dst=None):
+        dst = np.empty(self.output_floats, dtype=np.float32) if dst is None else dst
+        _lib.check(self.ctx.lib.b200msdf_batch_download(self.ctx.h, self.h, dst.ctypes.data_as(C.POINTER(C.c_float))))
+        return dst
+
+    def glyph(self, flat, g):
+        w, h = self.dims[g if len(self.dims) > 1 else 0]
+        n = CHANNELS[self.mode]
+        o = self.glyph_offset(g)
+        return flat[o:o + w * h * n].reshape(h, w, n)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.b200msdf_batch_free(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---- module-level functions named like the reference's -------------------------------------------------------------------
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def generateSDF(output, shape, transformation, config=None, **kw):
+    return default_context().generate(SDF, output, shape, transformation, config, **kw)
+
+
+def generatePSDF(output, shape, transformation, config=None, **kw):
+    return default_context().generate(PSDF, output, shape, transformation, config, **kw)
+
+
+generatePseudoSDF = generatePSDF
+
+
+def generateMSDF(output, shape, transformation, config=None, **kw):
+    return default_context().generate(MSDF, output, shape, transformation, config, **kw)
+
+
+def generateMTSDF(output, shape, transformation, config=None, **kw):
+    return default_context().generate(MTSDF, output, shape, transformation, config, **kw)
+
+
+def msdfErrorCorrection(sdf, shape, transformation, config=None, **kw):
+    return default_context().error_correction([sdf], shape, transformation, config, **kw)[0]
+
+
+def msdfFastDistanceErrorCorrection(sdf, transformation, minDeviationRatio=DEFAULT_RATIO):
+    return default_context().fast_error_correction(sdf, transformation, False, minDeviationRatio)
+
+
+def msdfFastEdgeErrorCorrection(sdf, transformation, minDeviationRatio=DEFAULT_RATIO):
+    return default_context().fast_error_correction(sdf, transformation, True, minDeviationRatio)

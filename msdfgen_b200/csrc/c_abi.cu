@@ -1,0 +1,666 @@
+// c_abi.cu — implementation of include/msdfgen_b200.h: context, HBM-resident batches, launches, host<->device transfers.
+// No torch, no oracle, no CPU compute path: every entry point that produces texels does so with the sm_100a kernels in
+// kernels.cuh or fails.
+#include "../../include/msdfgen_b200.h"
+#include "kernels.cuh"
+
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(B200MSDF_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap)
+            return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes+bytes/4+256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B200MSDF_ERR_ALLOC, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap)
+            return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes+bytes/4+256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B200MSDF_ERR_ALLOC, "cudaHostAlloc(%zu): %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+inline int channels_of(int mode) { return mode == B200MSDF_MSDF ? 3 : mode == B200MSDF_MTSDF ? 4 : 1; }
+
+}  // namespace
+
+struct b200msdf_batch {
+    int mode = 0, N = 0;
+    int nGlyphs = 0, nContours = 0, nSegments = 0, nTiles = 0;
+    int nBig = 0;
+    size_t nBigRecs = 0;
+    size_t outFloats = 0, texels = 0;
+    int maxContours = 0;
+    bool hasColors = false;
+    bool launched = false;
+    bool ecRan = false;
+    DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, field, out, stencil;
+    std::vector<GlyphDesc> hGlyphs;
+    std::vector<TileDesc> hTiles;
+    std::vector<int> hBig;
+    void release() {
+        points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
+        bigGlyphs.release(); bigRecs.release(); field.release(); out.release(); stencil.release();
+    }
+};
+
+struct b200msdf_ctx {
+    int device = 0;
+    int numSMs = 0;
+    cudaStream_t own = nullptr, stream = nullptr;
+    DevBuf counters, scratch;
+    PinBuf pinOut, pinIn;
+    uint64_t launches = 0;
+    b200msdf_batch pool;    // reused by the host-buffer entry points
+};
+
+namespace {
+
+int bind(b200msdf_ctx *ctx) {
+    if (!ctx)
+        return fail(B200MSDF_ERR_ARG, "null context");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return 0;
+}
+
+int check_shapes(const b200msdf_shapes *s) {
+    if (!s)
+        return fail(B200MSDF_ERR_ARG, "null shapes");
+    if (s->n_glyphs < 0 || s->n_contours < 0 || s->n_segments < 0)
+        return fail(B200MSDF_ERR_ARG, "negative counts");
+    if (s->n_glyphs > 0 && !s->glyph_contour_begin)
+        return fail(B200MSDF_ERR_ARG, "glyph_contour_begin is null");
+    if ((s->n_contours > 0 || s->n_glyphs > 0) && !s->contour_segment_begin)
+        return fail(B200MSDF_ERR_ARG, "contour_segment_begin is null");
+    if (s->n_segments > 0 && (!s->points || !s->orders))
+        return fail(B200MSDF_ERR_ARG, "points/orders are null");
+    for (int g = 0; g < s->n_glyphs; ++g)
+        if (s->glyph_contour_begin[g] > s->glyph_contour_begin[g+1])
+            return fail(B200MSDF_ERR_ARG, "glyph_contour_begin not monotonic at %d", g);
+    if (s->n_glyphs > 0 && s->glyph_contour_begin[s->n_glyphs] > (uint32_t) s->n_contours)
+        return fail(B200MSDF_ERR_ARG, "glyph_contour_begin exceeds n_contours");
+    for (int c = 0; c < s->n_contours; ++c)
+        if (s->contour_segment_begin[c] > s->contour_segment_begin[c+1])
+            return fail(B200MSDF_ERR_ARG, "contour_segment_begin not monotonic at %d", c);
+    if (s->contour_segment_begin && s->contour_segment_begin[s->n_contours] > (uint32_t) s->n_segments)
+        return fail(B200MSDF_ERR_ARG, "contour_segment_begin exceeds n_segments");
+    return 0;
+}
+
+// Builds per-glyph descriptors + tiles and uploads everything. flips[g] = output orientation != shape orientation.
+int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_shapes *s, const b200msdf_transform *xf, int xfPerGlyph,
+                 const int32_t *dims, int dimsPerGlyph, const uint8_t *outYDown) {
+    if (mode < 1 || mode > 4)
+        return fail(B200MSDF_ERR_ARG, "mode %d out of range", mode);
+    int rc = check_shapes(s);
+    if (rc) return rc;
+    if (!xf || !dims)
+        return fail(B200MSDF_ERR_ARG, "null transformation/dims");
+    b->mode = mode;
+    b->N = channels_of(mode);
+    b->nGlyphs = s->n_glyphs;
+    b->nContours = s->n_contours;
+    b->nSegments = s->n_segments;
+    b->hasColors = s->colors != nullptr;
+    b->launched = false;
+    b->hGlyphs.resize((size_t) s->n_glyphs);
+    b->hTiles.clear();
+    b->hBig.clear();
+    size_t outFloats = 0, texels = 0, bigRecs = 0;
+    int maxContours = 0;
+    for (int g = 0; g < s->n_glyphs; ++g) {
+        GlyphDesc &d = b->hGlyphs[(size_t) g];
+        const b200msdf_transform &t = xf[xfPerGlyph ? g : 0];
+        d.sx = t.scale_x; d.sy = t.scale_y; d.tx = t.translate_x; d.ty = t.translate_y;
+        d.dmScale = t.dm_scale; d.dmTranslate = t.dm_translate;
+        d.w = dims[dimsPerGlyph ? 2*g : 0];
+        d.h = dims[dimsPerGlyph ? 2*g+1 : 1];
+        if (d.w < 0 || d.h < 0 || (long long) d.w*d.h > (long long) UINT_MAX-TILE_PIXELS)
+            return fail(B200MSDF_ERR_ARG, "bad dimensions for glyph %d", g);
+        d.c0 = s->glyph_contour_begin[g];
+        d.c1 = s->glyph_contour_begin[g+1];
+        d.s0 = s->contour_segment_begin[d.c0];
+        d.s1 = s->contour_segment_begin[d.c1];
+        int nonEmpty = 0;
+        for (unsigned c = d.c0; c < d.c1; ++c)
+            nonEmpty += s->contour_segment_begin[c+1] > s->contour_segment_begin[c];
+        d.nonEmptyContours = nonEmpty;
+        if (nonEmpty > maxContours) maxContours = nonEmpty;
+        d.shapeYDown = s->y_downward ? (s->y_downward[g] != 0) : 0;
+        int oyd = outYDown ? (outYDown[g] != 0) : 0;
+        d.flip = oyd != d.shapeYDown;
+        d.outOffset = outFloats;
+        d.texelOffset = texels;
+        size_t px = (size_t) d.w*(size_t) d.h;
+        outFloats += (px*(size_t) b->N+3)&~size_t(3);
+        texels += px;
+        unsigned nSeg = d.s1-d.s0;
+        if (nSeg > SMEM_RECORDS) {
+            d.recBase = (int) bigRecs;
+            bigRecs += nSeg;
+            b->hBig.push_back(g);
+        } else
+            d.recBase = -1;
+        for (size_t p0 = 0; p0 < px; p0 += TILE_PIXELS) {
+            TileDesc td;
+            td.glyph = (unsigned) g;
+            td.pix0 = (unsigned) p0;
+            b->hTiles.push_back(td);
+        }
+    }
+    b->outFloats = outFloats;
+    b->texels = texels;
+    b->maxContours = maxContours;
+    b->nTiles = (int) b->hTiles.size();
+    b->nBig = (int) b->hBig.size();
+    b->nBigRecs = bigRecs;
+
+    cudaStream_t st = ctx->stream;
+    size_t nSeg = (size_t) s->n_segments, nCon = (size_t) s->n_contours;
+    if ((rc = b->points.reserve(nSeg*64+64))) return rc;
+    if ((rc = b->orders.reserve(nSeg+16))) return rc;
+    if ((rc = b->colors.reserve(nSeg+16))) return rc;
+    if ((rc = b->cbegin.reserve((nCon+1)*4))) return rc;
+    if ((rc = b->windings.reserve(nCon+16))) return rc;
+    if ((rc = b->glyphs.reserve(sizeof(GlyphDesc)*(b->hGlyphs.size()+1)))) return rc;
+    if ((rc = b->tiles.reserve(sizeof(TileDesc)*(b->hTiles.size()+1)))) return rc;
+    if ((rc = b->out.reserve(outFloats*4+64))) return rc;
+    if (b->N >= 3) {
+        if ((rc = b->field.reserve(outFloats*4+64))) return rc;
+        if ((rc = b->stencil.reserve(texels+64))) return rc;
+    }
+    if (b->nBig) {
+        if ((rc = b->bigGlyphs.reserve(sizeof(int)*b->hBig.size()))) return rc;
+        if ((rc = b->bigRecs.reserve(sizeof(SegRec)*bigRecs))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b->bigGlyphs.p, b->hBig.data(), sizeof(int)*b->hBig.size(), cudaMemcpyHostToDevice, st));
+    }
+    if (nSeg) {
+        CUDA_TRY(cudaMemcpyAsync(b->points.p, s->points, nSeg*64, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->orders.p, s->orders, nSeg, cudaMemcpyHostToDevice, st));
+        if (s->colors)
+            CUDA_TRY(cudaMemcpyAsync(b->colors.p, s->colors, nSeg, cudaMemcpyHostToDevice, st));
+    }
+    if (s->contour_segment_begin)
+        CUDA_TRY(cudaMemcpyAsync(b->cbegin.p, s->contour_segment_begin, (nCon+1)*4, cudaMemcpyHostToDevice, st));
+    else
+        CUDA_TRY(cudaMemsetAsync(b->cbegin.p, 0, 4, st));
+    if (!b->hGlyphs.empty())
+        CUDA_TRY(cudaMemcpyAsync(b->glyphs.p, b->hGlyphs.data(), sizeof(GlyphDesc)*b->hGlyphs.size(), cudaMemcpyHostToDevice, st));
+    if (!b->hTiles.empty())
+        CUDA_TRY(cudaMemcpyAsync(b->tiles.p, b->hTiles.data(), sizeof(TileDesc)*b->hTiles.size(), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+template <typename K>
+int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, int *grid) {
+    int perSM = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, CTA_THREADS, 0));
+    if (perSM < 1) perSM = 1;
+    long long g = (long long) perSM*ctx->numSMs;
+    *grid = (int) (g < nTiles ? g : nTiles);
+    if (*grid < 1) *grid = 1;
+    return 0;
+}
+
+template <typename K>
+int launch_tiles(b200msdf_ctx *ctx, K kernel, KernelParams &P, int perThreadDoubles) {
+    int grid = 1, rc;
+    if ((rc = grid_for(ctx, kernel, P.nTiles, &grid))) return rc;
+    P.scratchStride = (size_t) grid*CTA_THREADS;
+    if (perThreadDoubles > 0) {
+        if ((rc = ctx->scratch.reserve(P.scratchStride*(size_t) perThreadDoubles*sizeof(double)))) return rc;
+        P.scratch = ctx->scratch.as<double>();
+    } else
+        P.scratch = nullptr;
+    kernel<<<grid, CTA_THREADS, 0, ctx->stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    ++ctx->launches;
+    return 0;
+}
+
+int launch_k1(b200msdf_ctx *ctx, int mode, bool overlap, KernelParams &P, int maxContours) {
+    int nout = channels_of(mode);
+    int scratch = (overlap && maxContours > B200_LOCAL_CONTOURS) ? maxContours*nout : 0;
+    switch (mode*2+(overlap ? 1 : 0)) {
+        case 2: return launch_tiles(ctx, k1_distance_field<1, false>, P, scratch);
+        case 3: return launch_tiles(ctx, k1_distance_field<1, true>, P, scratch);
+        case 4: return launch_tiles(ctx, k1_distance_field<2, false>, P, scratch);
+        case 5: return launch_tiles(ctx, k1_distance_field<2, true>, P, scratch);
+        case 6: return launch_tiles(ctx, k1_distance_field<3, false>, P, scratch);
+        case 7: return launch_tiles(ctx, k1_distance_field<3, true>, P, scratch);
+        case 8: return launch_tiles(ctx, k1_distance_field<4, false>, P, scratch);
+        case 9: return launch_tiles(ctx, k1_distance_field<4, true>, P, scratch);
+    }
+    return fail(B200MSDF_ERR_ARG, "bad mode");
+}
+
+int launch_k2(b200msdf_ctx *ctx, int N, bool overlap, KernelParams &P, int maxContours) {
+    int scratch = (overlap && maxContours > B200_LOCAL_CONTOURS) ? maxContours : 0;
+    if (N == 3)
+        return overlap ? launch_tiles(ctx, k2_error_correction<3, true>, P, scratch) : launch_tiles(ctx, k2_error_correction<3, false>, P, scratch);
+    return overlap ? launch_tiles(ctx, k2_error_correction<4, true>, P, scratch) : launch_tiles(ctx, k2_error_correction<4, false>, P, scratch);
+}
+
+void fill_params(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cfg, KernelParams &P) {
+    memset(&P, 0, sizeof(P));
+    P.raw.points = b->points.as<double>();
+    P.raw.orders = b->orders.as<uint8_t>();
+    P.raw.colors = b->hasColors ? b->colors.as<uint8_t>() : nullptr;
+    P.raw.cbegin = b->cbegin.as<uint32_t>();
+    P.raw.windings = b->windings.as<int8_t>();
+    P.glyphs = b->glyphs.as<GlyphDesc>();
+    P.tiles = b->tiles.as<TileDesc>();
+    P.nTiles = b->nTiles;
+    P.nContours = b->nContours;
+    P.bigRecs = b->bigRecs.as<SegRec>();
+    P.counters = ctx->counters.as<int>();
+    P.ecMode = cfg->ec_mode;
+    P.ecDcm = cfg->ec_distance_check_mode;
+    P.minDeviationRatio = cfg->min_deviation_ratio;
+    P.minImproveRatio = cfg->min_improve_ratio;
+}
+
+// windings (+ counter reset) and big-shape record preparation
+int launch_prologue(b200msdf_ctx *ctx, b200msdf_batch *b, KernelParams &P) {
+    int blocks = (b->nContours+127)/128;
+    if (blocks < 1) blocks = 1;
+    k0_windings<<<blocks, 128, 0, ctx->stream>>>(P.raw, b->nContours, b->windings.as<int8_t>(), P.counters);
+    CUDA_TRY(cudaGetLastError());
+    ++ctx->launches;
+    if (b->nBig) {
+        dim3 grid(64, (unsigned) (b->nBig < 1024 ? b->nBig : 1024));
+        k0_prepare_big<<<grid, 128, 0, ctx->stream>>>(P.raw, P.glyphs, b->bigGlyphs.as<int>(), b->nBig, b->bigRecs.as<SegRec>());
+        CUDA_TRY(cudaGetLastError());
+        ++ctx->launches;
+    }
+    return 0;
+}
+
+int check_config(const b200msdf_config *cfg) {
+    if (!cfg)
+        return fail(B200MSDF_ERR_ARG, "null config");
+    if (cfg->ec_mode < 0 || cfg->ec_mode > 3 || cfg->ec_distance_check_mode < 0 || cfg->ec_distance_check_mode > 2)
+        return fail(B200MSDF_ERR_ARG, "error-correction mode out of range");
+    return 0;
+}
+
+int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cfg) {
+    int rc = check_config(cfg);
+    if (rc) return rc;
+    if (b->nGlyphs == 0 || b->nTiles == 0) {
+        b->launched = true;
+        return 0;
+    }
+    KernelParams P;
+    fill_params(ctx, b, cfg, P);
+    bool ec = b->N >= 3 && cfg->ec_mode != B200MSDF_EC_DISABLED;
+    P.field = ec ? b->field.as<float>() : b->out.as<float>();
+    P.out = b->out.as<float>();
+    P.stencil = ec ? b->stencil.as<uint8_t>() : nullptr;
+    if ((rc = launch_prologue(ctx, b, P))) return rc;
+    if ((rc = launch_k1(ctx, b->mode, cfg->overlap_support != 0, P, b->maxContours))) return rc;
+    if (ec)
+        if ((rc = launch_k2(ctx, b->N, cfg->overlap_support != 0, P, b->maxContours))) return rc;
+    b->launched = true;
+    b->ecRan = ec;
+    return 0;
+}
+
+// Copies device results (src: device pointer to the packed output) to caller bitmaps.
+int download_to_bitmaps(b200msdf_ctx *ctx, b200msdf_batch *b, const float *dSrc, const b200msdf_bitmap *bm) {
+    if (b->nGlyphs == 0 || b->outFloats == 0)
+        return 0;
+    int N = b->N;
+    // Fast path: the caller's sections are one packed block in device layout -> a single DMA straight into it.
+    bool packed = true;
+    for (int g = 0; g < b->nGlyphs && packed; ++g) {
+        const GlyphDesc &d = b->hGlyphs[(size_t) g];
+        if ((size_t) d.w*d.h == 0)
+            continue;
+        if (bm[g].row_stride != d.w*N || bm[g].pixels != bm[0].pixels+(d.outOffset-b->hGlyphs[0].outOffset))
+            packed = false;
+    }
+    if (packed && bm[0].pixels) {
+        const GlyphDesc &last = b->hGlyphs[(size_t) b->nGlyphs-1];
+        size_t floats = last.outOffset+(size_t) last.w*last.h*N;
+        CUDA_TRY(cudaMemcpyAsync(bm[0].pixels, dSrc, floats*4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    }
+    int rc = ctx->pinOut.reserve(b->outFloats*4);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx->pinOut.p, dSrc, b->outFloats*4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const float *h = static_cast<const float *>(ctx->pinOut.p);
+    for (int g = 0; g < b->nGlyphs; ++g) {
+        const GlyphDesc &d = b->hGlyphs[(size_t) g];
+        if (!bm[g].pixels)
+            continue;
+        for (int r = 0; r < d.h; ++r)
+            memcpy(bm[g].pixels+(ptrdiff_t) bm[g].row_stride*r, h+d.outOffset+(size_t) r*d.w*N, sizeof(float)*(size_t) d.w*N);
+    }
+    return 0;
+}
+
+int check_bitmaps(const b200msdf_bitmap *bm, int n) {
+    if (n > 0 && !bm)
+        return fail(B200MSDF_ERR_ARG, "null outputs");
+    for (int g = 0; g < n; ++g) {
+        if (bm[g].width < 0 || bm[g].height < 0)
+            return fail(B200MSDF_ERR_ARG, "negative bitmap size at %d", g);
+        if ((size_t) bm[g].width*bm[g].height > 0 && !bm[g].pixels)
+            return fail(B200MSDF_ERR_ARG, "null pixels at %d", g);
+    }
+    return 0;
+}
+
+void dims_from_bitmaps(const b200msdf_bitmap *bm, int n, std::vector<int32_t> &dims, std::vector<uint8_t> &yd) {
+    dims.resize((size_t) n*2);
+    yd.resize((size_t) n);
+    for (int g = 0; g < n; ++g) {
+        dims[2*(size_t) g] = bm[g].width;
+        dims[2*(size_t) g+1] = bm[g].height;
+        yd[(size_t) g] = bm[g].y_downward != 0;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200msdf_version(void) { return B200MSDF_VERSION; }
+
+const char *b200msdf_last_error(void) { return g_error.c_str(); }
+
+void b200msdf_default_config(b200msdf_config *cfg) {
+    if (!cfg) return;
+    cfg->overlap_support = 1;
+    cfg->ec_mode = B200MSDF_EC_EDGE_PRIORITY;
+    cfg->ec_distance_check_mode = B200MSDF_DCM_CHECK_AT_EDGE;
+    cfg->min_deviation_ratio = 1.11111111111111111;
+    cfg->min_improve_ratio = 1.11111111111111111;
+    cfg->ec_buffer = nullptr;
+}
+
+int b200msdf_create(int device, b200msdf_ctx **out) {
+    if (!out)
+        return fail(B200MSDF_ERR_ARG, "null ctx pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(B200MSDF_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device < 0 || device >= count)
+        return fail(B200MSDF_ERR_ARG, "device %d out of range (%d devices)", device, count);
+    CUDA_TRY(cudaSetDevice(device));
+    b200msdf_ctx *ctx = new (std::nothrow) b200msdf_ctx;
+    if (!ctx)
+        return fail(B200MSDF_ERR_ALLOC, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete ctx; return fail(B200MSDF_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    ctx->numSMs = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return fail(B200MSDF_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    ctx->stream = ctx->own;
+    int rc = ctx->counters.reserve(64);
+    if (rc) { cudaStreamDestroy(ctx->own); delete ctx; return rc; }
+    *out = ctx;
+    return 0;
+}
+
+void b200msdf_destroy(b200msdf_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->pool.release();
+    ctx->counters.release();
+    ctx->scratch.release();
+    ctx->pinOut.release();
+    ctx->pinIn.release();
+    if (ctx->own) cudaStreamDestroy(ctx->own);
+    delete ctx;
+}
+
+int b200msdf_set_stream(b200msdf_ctx *ctx, void *cuda_stream) {
+    if (!ctx)
+        return fail(B200MSDF_ERR_ARG, "null context");
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own;
+    return 0;
+}
+
+int b200msdf_synchronize(b200msdf_ctx *ctx) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+uint64_t b200msdf_launch_count(const b200msdf_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int b200msdf_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr)
+        return fail(B200MSDF_ERR_ARG, "null pointer");
+    *ptr = nullptr;
+    cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B200MSDF_ERR_ALLOC, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+void b200msdf_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+int b200msdf_generate_batch(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
+                            const b200msdf_bitmap *outputs, const b200msdf_config *config) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_shapes(shapes))) return rc;
+    if ((rc = check_config(config))) return rc;
+    if ((rc = check_bitmaps(outputs, shapes->n_glyphs))) return rc;
+    if (shapes->n_glyphs == 0)
+        return 0;
+    std::vector<int32_t> dims;
+    std::vector<uint8_t> yd;
+    dims_from_bitmaps(outputs, shapes->n_glyphs, dims, yd);
+    b200msdf_batch *b = &ctx->pool;
+    if ((rc = upload_batch(ctx, b, mode, shapes, xf, xfPerGlyph, dims.data(), 1, yd.data()))) return rc;
+    if ((rc = launch_batch(ctx, b, config))) return rc;
+    if ((rc = download_to_bitmaps(ctx, b, b->out.as<float>(), outputs))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200msdf_generate(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shape, const b200msdf_transform *xf, const b200msdf_bitmap *output,
+                      const b200msdf_config *config) {
+    if (!shape || shape->n_glyphs != 1)
+        return fail(B200MSDF_ERR_ARG, "b200msdf_generate takes exactly one shape");
+    int rc = b200msdf_generate_batch(ctx, mode, shape, xf, 0, output, config);
+    if (rc) return rc;
+    if (config->ec_buffer && mode >= 3 && config->ec_mode != B200MSDF_EC_DISABLED && ctx->pool.texels) {
+        CUDA_TRY(cudaMemcpyAsync(config->ec_buffer, ctx->pool.stencil.p, ctx->pool.texels, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+static int ec_common(b200msdf_ctx *ctx, int channels, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
+                     const b200msdf_bitmap *sdfs, const b200msdf_config *config, int shapeless) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (channels != 3 && channels != 4)
+        return fail(B200MSDF_ERR_ARG, "error correction needs 3 or 4 channels");
+    if ((rc = check_shapes(shapes))) return rc;
+    if ((rc = check_config(config))) return rc;
+    if ((rc = check_bitmaps(sdfs, shapes->n_glyphs))) return rc;
+    if (shapes->n_glyphs == 0 || config->ec_mode == B200MSDF_EC_DISABLED)
+        return 0;
+    std::vector<int32_t> dims;
+    std::vector<uint8_t> yd;
+    dims_from_bitmaps(sdfs, shapes->n_glyphs, dims, yd);
+    b200msdf_batch *b = &ctx->pool;
+    int mode = channels == 3 ? B200MSDF_MSDF : B200MSDF_MTSDF;
+    if (shapeless) {
+        // msdfErrorCorrectionShapeless works in the sdf's own orientation: present the (empty) shape with the same orientation
+        for (int g = 0; g < shapes->n_glyphs; ++g) yd[(size_t) g] = 0;
+    }
+    if ((rc = upload_batch(ctx, b, mode, shapes, xf, xfPerGlyph, dims.data(), 1, yd.data()))) return rc;
+    // gather the caller's fields into the device layout
+    if ((rc = ctx->pinIn.reserve(b->outFloats*4))) return rc;
+    float *h = static_cast<float *>(ctx->pinIn.p);
+    for (int g = 0; g < b->nGlyphs; ++g) {
+        const GlyphDesc &d = b->hGlyphs[(size_t) g];
+        for (int r = 0; r < d.h; ++r)
+            memcpy(h+d.outOffset+(size_t) r*d.w*channels, sdfs[g].pixels+(ptrdiff_t) sdfs[g].row_stride*r, sizeof(float)*(size_t) d.w*channels);
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->field.p, h, b->outFloats*4, cudaMemcpyHostToDevice, ctx->stream));
+    KernelParams P;
+    fill_params(ctx, b, config, P);
+    P.field = b->field.as<float>();
+    P.out = b->out.as<float>();
+    P.stencil = b->stencil.as<uint8_t>();
+    P.shapeless = shapeless;
+    if ((rc = launch_prologue(ctx, b, P))) return rc;
+    if ((rc = launch_k2(ctx, channels, config->overlap_support != 0, P, b->maxContours))) return rc;
+    if ((rc = download_to_bitmaps(ctx, b, b->out.as<float>(), sdfs))) return rc;
+    if (!shapeless && config->ec_buffer && shapes->n_glyphs == 1 && b->texels) {
+        CUDA_TRY(cudaMemcpyAsync(config->ec_buffer, b->stencil.p, b->texels, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200msdf_error_correction(b200msdf_ctx *ctx, int channels, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
+                              const b200msdf_bitmap *sdfs, const b200msdf_config *config) {
+    return ec_common(ctx, channels, shapes, xf, xfPerGlyph, sdfs, config, 0);
+}
+
+int b200msdf_fast_error_correction(b200msdf_ctx *ctx, int channels, int edge, const b200msdf_transform *xf, const b200msdf_bitmap *sdf,
+                                   double min_deviation_ratio) {
+    static const uint32_t zero[2] = { 0, 0 };
+    b200msdf_shapes empty;
+    memset(&empty, 0, sizeof(empty));
+    empty.n_glyphs = 1;
+    empty.glyph_contour_begin = zero;
+    empty.contour_segment_begin = zero;
+    b200msdf_config cfg;
+    b200msdf_default_config(&cfg);
+    cfg.ec_mode = edge ? B200MSDF_EC_EDGE_ONLY : B200MSDF_EC_INDISCRIMINATE;   // protectAll or nothing (msdf-error-correction.cpp:51-59)
+    cfg.ec_distance_check_mode = B200MSDF_DCM_DO_NOT_CHECK;
+    cfg.min_deviation_ratio = min_deviation_ratio;
+    return ec_common(ctx, channels, &empty, xf, 0, sdf, &cfg, 1);
+}
+
+int b200msdf_batch_upload(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
+                          const int32_t *dims, int dimsPerGlyph, const uint8_t *outYDown, b200msdf_batch **out) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!out)
+        return fail(B200MSDF_ERR_ARG, "null batch pointer");
+    *out = nullptr;
+    b200msdf_batch *b = new (std::nothrow) b200msdf_batch;
+    if (!b)
+        return fail(B200MSDF_ERR_ALLOC, "out of host memory");
+    rc = upload_batch(ctx, b, mode, shapes, xf, xfPerGlyph, dims, dimsPerGlyph, outYDown);
+    if (rc) {
+        b->release();
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return 0;
+}
+
+int b200msdf_batch_launch(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200msdf_config *config) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!batch)
+        return fail(B200MSDF_ERR_ARG, "null batch");
+    return launch_batch(ctx, batch, config);
+}
+
+float *b200msdf_batch_device_output(const b200msdf_batch *batch) { return batch ? batch->out.as<float>() : nullptr; }
+uint8_t *b200msdf_batch_device_stencil(const b200msdf_batch *batch) { return batch ? batch->stencil.as<uint8_t>() : nullptr; }
+size_t b200msdf_batch_output_floats(const b200msdf_batch *batch) { return batch ? batch->outFloats : 0; }
+size_t b200msdf_batch_glyph_offset(const b200msdf_batch *batch, int glyph) {
+    if (!batch || glyph < 0 || glyph >= batch->nGlyphs) return 0;
+    return batch->hGlyphs[(size_t) glyph].outOffset;
+}
+
+int b200msdf_batch_download(b200msdf_ctx *ctx, b200msdf_batch *batch, float *host_dst) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!batch || !host_dst)
+        return fail(B200MSDF_ERR_ARG, "null batch/destination");
+    if (batch->outFloats)
+        CUDA_TRY(cudaMemcpyAsync(host_dst, batch->out.p, batch->outFloats*4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void b200msdf_batch_free(b200msdf_ctx *ctx, b200msdf_batch *batch) {
+    if (!batch) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    batch->release();
+    delete batch;
+}
+
+}  // extern "C"

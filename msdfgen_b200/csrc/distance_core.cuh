@@ -1,0 +1,738 @@
+// distance_core.cuh — device-side geometry + selector + contour-combiner math for the sm_100a kernels.
+//
+// One thread owns one query point and walks the glyph's prepared segment records; all arithmetic on the distance path is
+// fp64 and the translation unit is compiled with -fmad=false so that every expression rounds exactly like the reference's
+// scalar C++ (which must itself be built without FMA contraction).
+//
+// Reference semantics restated here (paths relative to /root/reference/):
+//   segment distance kernels      core/edge-segments.cpp:173-277, direction/point :108-139, perpendicular conversion :28-52
+//   closed-form solvers           core/equation-solver.cpp:9-70
+//   selectors (cache-less)        core/edge-selectors.cpp:19-38 (true), :42-52,81-117,129-164 (perpendicular), :174-260 (multi)
+//   contour combiners             core/contour-combiners.cpp:34-50 (simple), :57-134 (overlapping)
+//   traversal order               core/ShapeDistanceFinder.hpp:36-58 (oneShotDistance: every edge evaluated, last edge first)
+// What is NOT the reference's structure: per-segment constants (unit tangents at both ends, corner bisectors, the cubic
+// coefficients of the quadratic-Bezier foot-point equation) are hoisted into a SegRec by one thread per segment instead of
+// being recomputed per pixel per edge (that recomputation is 42 % of the reference's profile); the
+// EdgeCache pruning is dropped (it is a serial-scan optimisation); per-contour selectors are streamed and folded into
+// shape/inner/outer accumulators instead of living in a std::vector.
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200 {
+
+struct d2 { double x, y; };
+
+__device__ __forceinline__ d2 mk(double x, double y) { d2 r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ d2 operator+(d2 a, d2 b) { return mk(a.x+b.x, a.y+b.y); }
+__device__ __forceinline__ d2 operator-(d2 a, d2 b) { return mk(a.x-b.x, a.y-b.y); }
+__device__ __forceinline__ d2 operator*(double s, d2 a) { return mk(s*a.x, s*a.y); }
+__device__ __forceinline__ double dot(d2 a, d2 b) { return a.x*b.x+a.y*b.y; }
+__device__ __forceinline__ double cross(d2 a, d2 b) { return a.x*b.y-a.y*b.x; }
+__device__ __forceinline__ double len(d2 a) { return sqrt(a.x*a.x+a.y*a.y); }
+__device__ __forceinline__ bool is_zero(d2 a) { return a.x == 0 && a.y == 0; }
+// Vector2::normalize(allowZero): zero vector -> (0, !allowZero)
+__device__ __forceinline__ d2 normalize(d2 a, bool allowZero) {
+    double l = len(a);
+    if (l != 0)
+        return mk(a.x/l, a.y/l);
+    return mk(0, allowZero ? 0.0 : 1.0);
+}
+// a/|a| when the length is already known (same sqrt value the reference recomputes)
+__device__ __forceinline__ d2 normalize_known(d2 a, double l) {
+    if (l != 0)
+        return mk(a.x/l, a.y/l);
+    return mk(0, 1.0);
+}
+// mix(a, b, w) = (1-w)*a + w*b
+__device__ __forceinline__ d2 mix(d2 a, d2 b, double w) { return mk((1.0-w)*a.x+w*b.x, (1.0-w)*a.y+w*b.y); }
+__device__ __forceinline__ double dmin(double a, double b) { return b < a ? b : a; }
+__device__ __forceinline__ double dmax(double a, double b) { return a < b ? b : a; }
+__device__ __forceinline__ double median3(double a, double b, double c) { return dmax(dmin(a, b), dmin(dmax(a, b), c)); }
+__device__ __forceinline__ float fmin2(float a, float b) { return b < a ? b : a; }
+__device__ __forceinline__ float fmax2(float a, float b) { return a < b ? b : a; }
+__device__ __forceinline__ float median3f(float a, float b, float c) { return fmax2(fmin2(a, b), fmin2(fmax2(a, b), c)); }
+// nonZeroSign(n)*m
+__device__ __forceinline__ double signed_by(double n, double m) { return n > 0 ? m : -m; }
+// SignedDistance operator<
+__device__ __forceinline__ bool sd_less(double ad, double adot, double bd, double bdot) {
+    double x = fabs(ad), y = fabs(bd);
+    return x < y || (x == y && adot < bdot);
+}
+
+enum : int {
+    SEG_LAST_IN_CONTOUR = 1,   // contour ends after this record (evaluation order)
+    SEG_CUBIC_NORMED = 2       // quadratic segment: foot-point cubic takes the normalised (trig/Cardano) branch
+};
+
+// One prepared edge segment, in EVALUATION order (per contour: last edge first, then edges 0..n-2).
+struct __align__(16) SegRec {
+    d2 p0, p1, p2, p3;     // control points (unused = 0)
+    d2 pEnd;               // point(1) = p[order]
+    d2 aDir, bDir;         // direction(0), direction(1), normalize(true)
+    d2 aBis, bBis;         // (prevDir+aDir).normalize(true), (bDir+nextDir).normalize(true)
+    d2 aDirNZ, bDirNZ;     // direction(0), direction(1), normalize()   (zero -> (0,1))
+    // type-specific constants:
+    //   linear:    e0,1 = ab   e2 = ab.ab   e3,4 = ab.getOrthonormal(false)
+    //   quadratic: e0,1 = ab   e2,3 = br    e4 = br.br  e5 = 3 ab.br  e6 = 2 ab.ab  e7,8 = direction(0)  e9 = its sq. length
+    //              e10,11 = direction(1)  e12 = its sq. length  e13 = e5/e4
+    //   cubic:     e0,1 = ab   e2,3 = br    e4,5 = as   e7..e12 as quadratic
+    double e[14];
+    int order;             // 1, 2, 3
+    int color;             // EdgeColor mask
+    int flags;
+    int winding;           // Contour::winding() of the owning contour
+    int cornerL, cornerB;  // texel l,b of protectCorners if this edge starts a colour corner, else INT_MIN/2
+    int storageIndex;      // index of the segment in the caller's arrays
+    int pad;
+};
+
+// Per-glyph geometry, built on the host when a batch is uploaded.
+struct GlyphDesc {
+    double sx, sy, tx, ty;          // Projection scale, translate
+    double dmScale, dmTranslate;    // DistanceMapping
+    unsigned long long outOffset;   // float offset of the glyph's [h][w][N] block in the output buffer
+    unsigned long long texelOffset; // texel offset (stencil buffer)
+    int w, h;
+    unsigned c0, c1;                // contour range
+    unsigned s0, s1;                // segment range (storage == evaluation range)
+    int flip;                       // output orientation != shape orientation (rows reversed in memory)
+    int shapeYDown;                 // Shape::inverseYAxis
+    int nonEmptyContours;
+    int recBase;                    // >= 0: prepared records live in the global big-shape buffer at this index; -1: staged in smem
+};
+
+struct RawShapes {
+    const double *points;
+    const uint8_t *orders;
+    const uint8_t *colors;      // may be null (all WHITE)
+    const uint32_t *cbegin;
+    const int8_t *windings;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Raw segment access (used by the per-segment preparation only)
+
+struct RawSeg { d2 p[4]; int order; };
+
+__device__ __forceinline__ RawSeg load_raw(const RawShapes &rs, unsigned s) {
+    RawSeg r;
+    const double2 *q = reinterpret_cast<const double2 *>(rs.points+8*size_t(s));
+    double2 a = q[0], b = q[1], c = q[2], d = q[3];
+    r.p[0] = mk(a.x, a.y); r.p[1] = mk(b.x, b.y); r.p[2] = mk(c.x, c.y); r.p[3] = mk(d.x, d.y);
+    r.order = rs.orders[s];
+    return r;
+}
+
+// EdgeSegment::point(param)
+__device__ inline d2 seg_point(const RawSeg &s, double t) {
+    if (s.order == 1)
+        return mix(s.p[0], s.p[1], t);
+    if (s.order == 2)
+        return mix(mix(s.p[0], s.p[1], t), mix(s.p[1], s.p[2], t), t);
+    d2 p12 = mix(s.p[1], s.p[2], t);
+    return mix(mix(mix(s.p[0], s.p[1], t), p12, t), mix(p12, mix(s.p[2], s.p[3], t), t), t);
+}
+
+// EdgeSegment::direction(param)
+__device__ inline d2 seg_direction(const RawSeg &s, double t) {
+    if (s.order == 1)
+        return s.p[1]-s.p[0];
+    if (s.order == 2) {
+        d2 tangent = mix(s.p[1]-s.p[0], s.p[2]-s.p[1], t);
+        if (is_zero(tangent))
+            return s.p[2]-s.p[0];
+        return tangent;
+    }
+    d2 tangent = mix(mix(s.p[1]-s.p[0], s.p[2]-s.p[1], t), mix(s.p[2]-s.p[1], s.p[3]-s.p[2], t), t);
+    if (is_zero(tangent)) {
+        if (t == 0) return s.p[2]-s.p[0];
+        if (t == 1) return s.p[3]-s.p[1];
+    }
+    return tangent;
+}
+
+// Contour::winding() for contour c (one thread).
+__device__ inline int contour_winding(const RawShapes &rs, unsigned c) {
+    unsigned b = rs.cbegin[c], e = rs.cbegin[c+1];
+    unsigned n = e-b;
+    if (n == 0)
+        return 0;
+    double total = 0;
+    #define B200_SHOELACE(A, B) (((B).x-(A).x)*((A).y+(B).y))
+    if (n == 1) {
+        RawSeg s = load_raw(rs, b);
+        d2 p = seg_point(s, 0), q = seg_point(s, 1/3.), r = seg_point(s, 2/3.);
+        total += B200_SHOELACE(p, q);
+        total += B200_SHOELACE(q, r);
+        total += B200_SHOELACE(r, p);
+    } else if (n == 2) {
+        RawSeg s0 = load_raw(rs, b), s1 = load_raw(rs, b+1);
+        d2 p = seg_point(s0, 0), q = seg_point(s0, .5), r = seg_point(s1, 0), t = seg_point(s1, .5);
+        total += B200_SHOELACE(p, q);
+        total += B200_SHOELACE(q, r);
+        total += B200_SHOELACE(r, t);
+        total += B200_SHOELACE(t, p);
+    } else {
+        d2 prev = seg_point(load_raw(rs, e-1), 0);
+        for (unsigned i = b; i < e; ++i) {
+            d2 cur = seg_point(load_raw(rs, i), 0);
+            total += B200_SHOELACE(prev, cur);
+            prev = cur;
+        }
+    }
+    #undef B200_SHOELACE
+    return (0 < total)-(total < 0);
+}
+
+// Builds the record for evaluation position j of a glyph (j counts from the glyph's first segment; positions map to
+// contours exactly like storage indices do, only rotated inside each contour: position k of a contour [b,e) is edge e-1
+// for k == 0 and edge b+k-1 otherwise — ShapeDistanceFinder.hpp:22-28).
+__device__ inline void prepare_record(const RawShapes &rs, const GlyphDesc &g, unsigned j, SegRec &out) {
+    unsigned s = g.s0+j;
+    // contour containing storage index s (contours of a glyph: [c0, c1))
+    unsigned lo = g.c0, hi = g.c1;
+    while (hi-lo > 1) {
+        unsigned mid = (lo+hi)>>1;
+        if (rs.cbegin[mid] <= s) lo = mid; else hi = mid;
+    }
+    // skip over empty contours that share the same begin offset: the binary search lands on the LAST contour whose begin <= s
+    unsigned c = lo;
+    unsigned b = rs.cbegin[c], e = rs.cbegin[c+1];
+    unsigned k = s-b;
+    unsigned cur = k == 0 ? e-1 : s-1;
+    unsigned prev = cur == b ? e-1 : cur-1;
+    unsigned next = cur == e-1 ? b : cur+1;
+    RawSeg sc = load_raw(rs, cur);
+    RawSeg sp = load_raw(rs, prev);
+    RawSeg sn = load_raw(rs, next);
+
+    out.p0 = sc.p[0];
+    out.p1 = sc.p[1];
+    out.p2 = sc.order >= 2 ? sc.p[2] : mk(0, 0);
+    out.p3 = sc.order >= 3 ? sc.p[3] : mk(0, 0);
+    out.pEnd = seg_point(sc, 1);
+    out.p0 = seg_point(sc, 0);    // point(0): identical to p[0] for finite input, kept literal
+    d2 dir0 = seg_direction(sc, 0), dir1 = seg_direction(sc, 1);
+    out.aDir = normalize(dir0, true);
+    out.bDir = normalize(dir1, true);
+    out.aDirNZ = normalize(dir0, false);
+    out.bDirNZ = normalize(dir1, false);
+    d2 prevDir = normalize(seg_direction(sp, 1), true);
+    d2 nextDir = normalize(seg_direction(sn, 0), true);
+    out.aBis = normalize(prevDir+out.aDir, true);
+    out.bBis = normalize(out.bDir+nextDir, true);
+    out.order = sc.order;
+    int color = rs.colors ? rs.colors[cur] : 7;
+    out.color = color;
+    int flags = (k == e-b-1) ? SEG_LAST_IN_CONTOUR : 0;
+    out.winding = rs.windings[c];
+    out.storageIndex = int(cur);
+    out.pad = 0;
+    #pragma unroll
+    for (int i = 0; i < 14; ++i)
+        out.e[i] = 0;
+    // p0 restored to the raw control point for the distance kernels (point(0) above only differs for non-finite input)
+    d2 P0 = sc.p[0], P1 = sc.p[1], P2 = sc.p[2], P3 = sc.p[3];
+    if (sc.order == 1) {
+        d2 ab = P1-P0;
+        out.e[0] = ab.x; out.e[1] = ab.y;
+        out.e[2] = dot(ab, ab);
+        double l = len(ab);
+        d2 on = l != 0 ? mk(ab.y/l, -ab.x/l) : mk(0, -1.0);    // getOrthonormal(false)
+        out.e[3] = on.x; out.e[4] = on.y;
+    } else {
+        d2 ab = P1-P0;
+        d2 br = P2-P1-ab;
+        out.e[0] = ab.x; out.e[1] = ab.y;
+        out.e[2] = br.x; out.e[3] = br.y;
+        out.e[7] = dir0.x; out.e[8] = dir0.y; out.e[9] = dot(dir0, dir0);
+        out.e[10] = dir1.x; out.e[11] = dir1.y; out.e[12] = dot(dir1, dir1);
+        if (sc.order == 2) {
+            double a = dot(br, br);
+            double bq = 3*dot(ab, br);
+            out.e[4] = a;
+            out.e[5] = bq;
+            out.e[6] = 2*dot(ab, ab);
+            if (a != 0) {
+                double bn = bq/a;
+                out.e[13] = bn;
+                if (fabs(bn) < 1e6)
+                    flags |= SEG_CUBIC_NORMED;
+            }
+        } else {
+            d2 as = (P3-P2)-(P2-P1)-br;
+            out.e[4] = as.x; out.e[5] = as.y;
+        }
+    }
+    out.flags = flags;
+    // protectCorners (MSDFErrorCorrection.cpp:121-151): corner where the colour changes between prev and cur
+    int prevColor = rs.colors ? rs.colors[prev] : 7;
+    int common = prevColor&color;
+    int cl = INT_MIN/2, cb = INT_MIN/2;
+    if (!(common&(common-1))) {
+        d2 c0 = out.p0;
+        double px = g.sx*(c0.x+g.tx), py = g.sy*(c0.y+g.ty);    // Projection::project
+        double fl = floor(px-.5), fb = floor(py-.5);
+        if (fl > -1e9 && fl < 1e9 && fb > -1e9 && fb < 1e9) {
+            cl = int(fl);
+            cb = int(fb);
+        }
+    }
+    out.cornerL = cl;
+    out.cornerB = cb;
+    out.p0 = P0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Closed-form solvers (equation-solver.cpp). Roots are returned in registers.
+
+struct Roots { double t0, t1, t2; int n; };
+
+__device__ __forceinline__ Roots solve_quadratic(double a, double b, double c) {
+    Roots r; r.t0 = r.t1 = r.t2 = 0; r.n = 0;
+    if (a == 0 || fabs(b) > 1e12*fabs(a)) {
+        if (b == 0) {
+            r.n = c == 0 ? -1 : 0;
+            return r;
+        }
+        r.t0 = -c/b;
+        r.n = 1;
+        return r;
+    }
+    double dscr = b*b-4*a*c;
+    if (dscr > 0) {
+        dscr = sqrt(dscr);
+        r.t0 = (-b+dscr)/(2*a);
+        r.t1 = (-b-dscr)/(2*a);
+        r.n = 2;
+    } else if (dscr == 0) {
+        r.t0 = -b/(2*a);
+        r.n = 1;
+    }
+    return r;
+}
+
+__device__ __forceinline__ Roots solve_cubic_normed(double a, double b, double c) {
+    Roots x; x.t0 = x.t1 = x.t2 = 0;
+    double a2 = a*a;
+    double q = 1/9.*(a2-3*b);
+    double r = 1/54.*(a*(2*a2-9*b)+27*c);
+    double r2 = r*r;
+    double q3 = q*q*q;
+    a *= 1/3.;
+    if (r2 < q3) {
+        double t = r/sqrt(q3);
+        if (t < -1) t = -1;
+        if (t > 1) t = 1;
+        t = acos(t);
+        q = -2*sqrt(q);
+        x.t0 = q*cos(1/3.*t)-a;
+        x.t1 = q*cos(1/3.*(t+2*3.14159265358979323846))-a;
+        x.t2 = q*cos(1/3.*(t-2*3.14159265358979323846))-a;
+        x.n = 3;
+    } else {
+        double u = (r < 0 ? 1 : -1)*pow(fabs(r)+sqrt(r2-q3), 1/3.);
+        double v = u == 0 ? 0 : q/u;
+        x.t0 = (u+v)-a;
+        if (u == v || fabs(u-v) < 1e-12*fabs(u+v)) {
+            x.t1 = -.5*(u+v)-a;
+            x.n = 2;
+        } else
+            x.n = 1;
+    }
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// EdgeSegment::signedDistance for the three segment types
+
+struct SDist { double d, dot, param; };
+
+__device__ __forceinline__ SDist sd_linear(const SegRec &s, d2 p) {
+    d2 aq = p-s.p0;
+    d2 ab = mk(s.e[0], s.e[1]);
+    SDist r;
+    r.param = dot(aq, ab)/s.e[2];
+    d2 ep = r.param > .5 ? s.p1 : s.p0;
+    d2 eq = ep-p;
+    double endpointDistance = len(eq);
+    if (r.param > 0 && r.param < 1) {
+        double ortho = dot(mk(s.e[3], s.e[4]), aq);
+        if (fabs(ortho) < endpointDistance) {
+            r.d = ortho;
+            r.dot = 0;
+            return r;
+        }
+    }
+    r.d = signed_by(cross(aq, ab), endpointDistance);
+    r.dot = fabs(dot(s.aDirNZ, normalize_known(eq, endpointDistance)));
+    return r;
+}
+
+__device__ __forceinline__ void quad_root(const SegRec &s, d2 p, d2 qa, d2 ab, d2 br, double t, double &minDistance, double &param) {
+    if (t > 0 && t < 1) {
+        d2 qe = qa+(2*t)*ab+(t*t)*br;
+        double distance = len(qe);
+        if (distance <= fabs(minDistance)) {
+            minDistance = signed_by(cross(ab+t*br, qe), distance);
+            param = t;
+        }
+    }
+}
+
+__device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p) {
+    d2 qa = s.p0-p;
+    d2 ab = mk(s.e[0], s.e[1]);
+    d2 br = mk(s.e[2], s.e[3]);
+    double a = s.e[4];
+    double b = s.e[5];
+    double c = s.e[6]+dot(qa, br);
+    double d = dot(qa, ab);
+    Roots t;
+    if (s.flags&SEG_CUBIC_NORMED)
+        t = solve_cubic_normed(s.e[13], c/a, d/a);
+    else
+        t = solve_quadratic(b, c, d);
+
+    d2 epDir = mk(s.e[7], s.e[8]);
+    double lenA = len(qa);
+    double minDistance = signed_by(cross(epDir, qa), lenA);
+    double param = -dot(qa, epDir)/s.e[9];
+    d2 qb = s.p2-p;
+    double lenB = len(qb);
+    if (lenB < fabs(minDistance)) {
+        epDir = mk(s.e[10], s.e[11]);
+        minDistance = signed_by(cross(epDir, qb), lenB);
+        param = dot(p-s.p1, epDir)/s.e[12];
+    }
+    if (t.n > 0) quad_root(s, p, qa, ab, br, t.t0, minDistance, param);
+    if (t.n > 1) quad_root(s, p, qa, ab, br, t.t1, minDistance, param);
+    if (t.n > 2) quad_root(s, p, qa, ab, br, t.t2, minDistance, param);
+
+    SDist r;
+    r.d = minDistance;
+    r.param = param;
+    if (param >= 0 && param <= 1)
+        r.dot = 0;
+    else if (param < .5)
+        r.dot = fabs(dot(s.aDirNZ, normalize_known(qa, lenA)));
+    else
+        r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
+    return r;
+}
+
+__device__ __noinline__ SDist sd_cubic(const SegRec &s, d2 p) {
+    d2 qa = s.p0-p;
+    d2 ab = mk(s.e[0], s.e[1]);
+    d2 br = mk(s.e[2], s.e[3]);
+    d2 as = mk(s.e[4], s.e[5]);
+
+    d2 epDir = mk(s.e[7], s.e[8]);
+    double lenA = len(qa);
+    double minDistance = signed_by(cross(epDir, qa), lenA);
+    double param = -dot(qa, epDir)/s.e[9];
+    d2 qb = s.p3-p;
+    double lenB = len(qb);
+    if (lenB < fabs(minDistance)) {
+        epDir = mk(s.e[10], s.e[11]);
+        minDistance = signed_by(cross(epDir, qb), lenB);
+        param = dot(epDir-qb, epDir)/s.e[12];
+    }
+    for (int i = 0; i <= 4; ++i) {      // MSDFGEN_CUBIC_SEARCH_STARTS
+        double t = 1./4*i;
+        d2 qe = qa+(3*t)*ab+(3*t*t)*br+(t*t*t)*as;
+        d2 d1 = 3*ab+(6*t)*br+(3*t*t)*as;
+        d2 d2v = 6*br+(6*t)*as;
+        double improvedT = t-dot(qe, d1)/(dot(d1, d1)+dot(qe, d2v));
+        if (improvedT > 0 && improvedT < 1) {
+            int remainingSteps = 4;     // MSDFGEN_CUBIC_SEARCH_STEPS
+            do {
+                t = improvedT;
+                qe = qa+(3*t)*ab+(3*t*t)*br+(t*t*t)*as;
+                d1 = 3*ab+(6*t)*br+(3*t*t)*as;
+                if (!--remainingSteps)
+                    break;
+                d2v = 6*br+(6*t)*as;
+                improvedT = t-dot(qe, d1)/(dot(d1, d1)+dot(qe, d2v));
+            } while (improvedT > 0 && improvedT < 1);
+            double distance = len(qe);
+            if (distance < fabs(minDistance)) {
+                minDistance = signed_by(cross(d1, qe), distance);
+                param = t;
+            }
+        }
+    }
+    SDist r;
+    r.d = minDistance;
+    r.param = param;
+    if (param >= 0 && param <= 1)
+        r.dot = 0;
+    else if (param < .5)
+        r.dot = fabs(dot(s.aDirNZ, normalize_known(qa, lenA)));
+    else
+        r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
+    return r;
+}
+
+__device__ __forceinline__ SDist signed_distance(const SegRec &s, d2 p) {
+    // s.order is uniform across the CTA (every thread walks the same record), so this switch does not diverge
+    if (s.order == 1)
+        return sd_linear(s, p);
+    if (s.order == 2)
+        return sd_quadratic(s, p);
+    return sd_cubic(s, p);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Selectors. MODE: 1 SDF (true distance), 2 PSDF (perpendicular), 3 MSDF (multi), 4 MTSDF (multi + true)
+
+template <int MODE> struct ModeTraits {
+    static const int NCH = MODE >= 3 ? 3 : 1;                   // selector channels
+    static const int NOUT = MODE == 3 ? 3 : MODE == 4 ? 4 : 1;  // distances per point
+};
+
+// PerpendicularDistanceSelectorBase state. `near` packs the nearest record index and on which side of [0,1] its
+// parameter fell (all that distanceToPerpendicularDistance needs): (index << 2) | side, side 1: param < 0, 2: param > 1.
+struct Chan {
+    double d, dot;      // minTrueDistance
+    double neg, pos;    // min negative / positive perpendicular distance
+    int near;           // -1 = NULL
+};
+
+__device__ __forceinline__ void chan_init(Chan &c) {
+    c.d = -DBL_MAX; c.dot = 0; c.neg = -DBL_MAX; c.pos = DBL_MAX; c.near = -1;
+}
+__device__ __forceinline__ void chan_add_perp(Chan &c, double x) {
+    if (x <= 0 && x > c.neg) c.neg = x;
+    if (x >= 0 && x < c.pos) c.pos = x;
+}
+template <bool PERP>
+__device__ __forceinline__ void chan_merge(Chan &c, const Chan &o) {
+    if (sd_less(o.d, o.dot, c.d, c.dot)) { c.d = o.d; c.dot = o.dot; c.near = o.near; }
+    if (PERP) {
+        if (o.neg > c.neg) c.neg = o.neg;
+        if (o.pos < c.pos) c.pos = o.pos;
+    }
+}
+// computeDistance
+__device__ __forceinline__ double chan_distance(const Chan &c, const SegRec *recs, d2 p) {
+    double m = c.d < 0 ? c.neg : c.pos;
+    if (c.near >= 0) {
+        double dd = c.d;
+        int side = c.near&3;
+        if (side) {
+            const SegRec &s = recs[c.near>>2];
+            if (side == 1) {
+                d2 aq = p-s.p0;
+                double ts = dot(aq, s.aDirNZ);
+                if (ts < 0) {
+                    double pd = cross(aq, s.aDirNZ);
+                    if (fabs(pd) <= fabs(dd))
+                        dd = pd;
+                }
+            } else {
+                d2 bq = p-s.pEnd;
+                double ts = dot(bq, s.bDirNZ);
+                if (ts > 0) {
+                    double pd = cross(bq, s.bDirNZ);
+                    if (fabs(pd) <= fabs(dd))
+                        dd = pd;
+                }
+            }
+        }
+        if (fabs(dd) < fabs(m))
+            m = dd;
+    }
+    return m;
+}
+
+template <int MODE> struct Sel { Chan ch[ModeTraits<MODE>::NCH]; };
+
+template <int MODE>
+__device__ __forceinline__ void sel_init(Sel<MODE> &s) {
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+        chan_init(s.ch[k]);
+}
+
+template <int MODE>
+__device__ __forceinline__ void sel_merge(Sel<MODE> &a, const Sel<MODE> &b) {
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+        chan_merge<MODE != 1>(a.ch[k], b.ch[k]);
+}
+
+template <int MODE>
+__device__ __forceinline__ void sel_distance(const Sel<MODE> &s, const SegRec *recs, d2 p, double *out) {
+    if (MODE == 1) {
+        out[0] = s.ch[0].d;
+        return;
+    }
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+        out[k] = chan_distance(s.ch[k], recs, p);
+    if (MODE == 4) {    // MultiDistanceSelector::trueDistance
+        double td = s.ch[0].d, tdot = s.ch[0].dot;
+        #pragma unroll
+        for (int k = 1; k < ModeTraits<MODE>::NCH; ++k)
+            if (sd_less(s.ch[k].d, s.ch[k].dot, td, tdot)) { td = s.ch[k].d; tdot = s.ch[k].dot; }
+        out[ModeTraits<MODE>::NOUT-1] = td;
+    }
+}
+
+// {True,Perpendicular,Multi}DistanceSelector::addEdge with every edge relevant
+template <int MODE>
+__device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, int recIndex, d2 p) {
+    SDist r = signed_distance(s, p);
+    if (MODE == 1) {
+        if (sd_less(r.d, r.dot, sel.ch[0].d, sel.ch[0].dot)) { sel.ch[0].d = r.d; sel.ch[0].dot = r.dot; }
+        return;
+    }
+    const int mask = MODE == 2 ? 1 : s.color;
+    int near = (recIndex<<2)|(r.param < 0 ? 1 : r.param > 1 ? 2 : 0);
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+        if (mask&(1<<k))
+            if (sd_less(r.d, r.dot, sel.ch[k].d, sel.ch[k].dot)) { sel.ch[k].d = r.d; sel.ch[k].dot = r.dot; sel.ch[k].near = near; }
+    d2 ap = p-s.p0;
+    d2 bp = p-s.pEnd;
+    double add = dot(ap, s.aBis);
+    double bdd = -dot(bp, s.bBis);
+    if (add > 0) {
+        // getPerpendicularDistance(pd, ap, -aDir) followed by pd = -pd; the two negations cancel exactly
+        double ts = -dot(ap, s.aDir);
+        if (ts > 0) {
+            double pd = cross(ap, s.aDir);
+            if (fabs(pd) < fabs(r.d)) {
+                #pragma unroll
+                for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+                    if (mask&(1<<k))
+                        chan_add_perp(sel.ch[k], pd);
+            }
+        }
+    }
+    if (bdd > 0) {
+        double ts = dot(bp, s.bDir);
+        if (ts > 0) {
+            double pd = cross(bp, s.bDir);
+            if (fabs(pd) < fabs(r.d)) {
+                #pragma unroll
+                for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+                    if (mask&(1<<k))
+                        chan_add_perp(sel.ch[k], pd);
+            }
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ double resolve(const double *d) {
+    return MODE >= 3 ? median3(d[0], d[1], d[2]) : d[0];
+}
+
+// Where the per-contour distances of the overlapping combiner live: a small per-thread array for typical glyphs, or a
+// slice of a global scratch buffer (stride = total threads) for shapes with many contours.
+#define B200_LOCAL_CONTOURS 4
+struct ContourStore {
+    double *base;
+    size_t stride;
+    __device__ __forceinline__ double &at(int contour, int k, int nout) { return base[(size_t(contour)*nout+k)*stride]; }
+};
+
+// ShapeDistanceFinder<Combiner<Selector>>::oneShotDistance at point p over the glyph's records [0, nRec).
+// recs is shared memory (small glyphs) or the global prepared buffer (big shapes); every thread of the CTA walks the same
+// record at the same time, so loads broadcast.  out gets NOUT raw (unmapped) fp64 distances.
+template <int MODE, bool OVERLAP>
+__device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, int nContours, d2 p, ContourStore store, double *out) {
+    const int NOUT = ModeTraits<MODE>::NOUT;
+    if (!OVERLAP) {
+        Sel<MODE> sel;
+        sel_init(sel);
+        for (int j = 0; j < nRec; ++j)
+            sel_add_edge<MODE>(sel, recs[j], j, p);
+        sel_distance<MODE>(sel, recs, p, out);
+        return;
+    }
+    Sel<MODE> cur, shape, inner, outer;
+    sel_init(cur); sel_init(shape); sel_init(inner); sel_init(outer);
+    int ci = 0;
+    for (int j = 0; j < nRec; ++j) {
+        const SegRec &s = recs[j];
+        sel_add_edge<MODE>(cur, s, j, p);
+        if (s.flags&SEG_LAST_IN_CONTOUR) {
+            double cd[NOUT];
+            sel_distance<MODE>(cur, recs, p, cd);
+            #pragma unroll
+            for (int k = 0; k < NOUT; ++k)
+                store.at(ci, k, NOUT) = cd[k];
+            sel_merge<MODE>(shape, cur);
+            double rd = resolve<MODE>(cd);
+            int w = s.winding;
+            if (w > 0 && rd >= 0)
+                sel_merge<MODE>(inner, cur);
+            if (w < 0 && rd <= 0)
+                sel_merge<MODE>(outer, cur);
+            sel_init(cur);
+            ++ci;
+        }
+    }
+    double shapeD[NOUT], innerD[NOUT], outerD[NOUT], dist[NOUT];
+    sel_distance<MODE>(shape, recs, p, shapeD);
+    sel_distance<MODE>(inner, recs, p, innerD);
+    sel_distance<MODE>(outer, recs, p, outerD);
+    double innerScalar = resolve<MODE>(innerD), outerScalar = resolve<MODE>(outerD);
+    int winding;
+    if (innerScalar >= 0 && fabs(innerScalar) <= fabs(outerScalar)) {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) dist[k] = innerD[k];
+        winding = 1;
+    } else if (outerScalar <= 0 && fabs(outerScalar) < fabs(innerScalar)) {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) dist[k] = outerD[k];
+        winding = -1;
+    } else {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) out[k] = shapeD[k];
+        return;
+    }
+    // The record that closes contour ci carries its winding; walk the closing records again (cheap: flags only).
+    // Pass 1: same-winding contours refine the inner/outer pick.  Pass 2: opposite/zero-winding contours may override it.
+    for (int pass = 0; pass < 2; ++pass) {
+        int c = 0;
+        for (int j = 0; j < nRec; ++j) {
+            if (!(recs[j].flags&SEG_LAST_IN_CONTOUR))
+                continue;
+            int w = recs[j].winding;
+            double cd[NOUT];
+            #pragma unroll
+            for (int k = 0; k < NOUT; ++k)
+                cd[k] = store.at(c, k, NOUT);
+            double rc = resolve<MODE>(cd), rdist = resolve<MODE>(dist);
+            bool take;
+            if (pass == 0) {
+                if (winding > 0)
+                    take = w > 0 && fabs(rc) < fabs(outerScalar) && rc > rdist;
+                else
+                    take = w < 0 && fabs(rc) < fabs(innerScalar) && rc < rdist;
+            } else
+                take = w != winding && rc*rdist >= 0 && fabs(rc) < fabs(rdist);
+            if (take) {
+                #pragma unroll
+                for (int k = 0; k < NOUT; ++k) dist[k] = cd[k];
+            }
+            ++c;
+        }
+    }
+    if (resolve<MODE>(dist) == resolve<MODE>(shapeD)) {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) dist[k] = shapeD[k];
+    }
+    #pragma unroll
+    for (int k = 0; k < NOUT; ++k) out[k] = dist[k];
+    (void) nContours;
+}
+
+}  // namespace b200
