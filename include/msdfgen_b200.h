@@ -103,7 +103,8 @@ const char *b200msdf_last_error(void);                       /* thread-local mes
 void b200msdf_default_config(b200msdf_config *cfg);          /* MSDFGeneratorConfig() defaults */
 int b200msdf_create(int device, b200msdf_ctx **ctx);         /* device = CUDA ordinal */
 void b200msdf_destroy(b200msdf_ctx *ctx);
-int b200msdf_set_stream(b200msdf_ctx *ctx, void *cuda_stream);   /* run on the caller's cudaStream_t (NULL = own stream) */
+/* Run on the caller's cudaStream_t (NULL = the CUDA default stream); use_own != 0 switches back to the context's own stream. */
+int b200msdf_set_stream(b200msdf_ctx *ctx, void *cuda_stream, int use_own);
 int b200msdf_synchronize(b200msdf_ctx *ctx);
 /* Number of kernels this context has launched so far (for bench.py's gpu_launches). */
 uint64_t b200msdf_launch_count(const b200msdf_ctx *ctx);

@@ -63,7 +63,7 @@ def load():
     lib.b200msdf_create.argtypes = [i32, C.POINTER(vp)]
     lib.b200msdf_destroy.argtypes = [vp]
     lib.b200msdf_destroy.restype = None
-    lib.b200msdf_set_stream.argtypes = [vp, vp]
+    lib.b200msdf_set_stream.argtypes = [vp, vp, i32]
     lib.b200msdf_synchronize.argtypes = [vp]
     lib.b200msdf_launch_count.argtypes = [vp]
     lib.b200msdf_launch_count.restype = u64

@@ -93,16 +93,42 @@ def _bitmap(a, ydown=False):
     return _lib.Bitmap(a.ctypes.data_as(C.POINTER(C.c_float)), w, h, a.strides[0] // 4, int(ydown))
 
 
+_BITMAP_DTYPE = np.dtype([("pixels", np.uint64), ("width", np.int32), ("height", np.int32), ("row_stride", np.int32), ("y_downward", np.int32)])
+
+
+def _bitmaps(outputs, n, ydown=None):
+    """b200msdf_bitmap[n] for a packed float32[n,h,w,N] block (vectorised) or a list of per-glyph arrays."""
+    if isinstance(outputs, np.ndarray) and outputs.ndim == 4:
+        assert outputs.dtype == np.float32 and outputs.shape[0] == n and outputs.strides[3] == 4 and outputs.strides[2] == 4 * outputs.shape[3]
+        rec = np.empty(max(n, 1), dtype=_BITMAP_DTYPE)
+        rec["pixels"][:n] = outputs.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(outputs.strides[0])
+        rec["width"], rec["height"], rec["row_stride"] = outputs.shape[2], outputs.shape[1], outputs.strides[1] // 4
+        rec["y_downward"] = 0
+        if ydown is not None:
+            rec["y_downward"][:n] = np.asarray(ydown, dtype=np.int32)
+        arr = (_lib.Bitmap * max(n, 1)).from_buffer(rec)
+        arr._keep = (rec, outputs)
+        return arr
+    bms = (_lib.Bitmap * max(n, 1))()
+    for g in range(n):
+        bms[g] = _bitmap(outputs[g], bool(ydown[g]) if ydown is not None else False)
+    return bms
+
+
 class Context:
     """One per thread and GPU (b200msdf_ctx): owns the stream and the pooled device / pinned buffers."""
 
     def __init__(self, device=0):
         self.lib = _lib.load()
         self.h = C.c_void_p()
+        self._pinned = []
         _lib.check(self.lib.b200msdf_create(device, C.byref(self.h)))
 
     def close(self):
         if self.h:
+            for p in self._pinned:
+                self.lib.b200msdf_host_free(p)
+            self._pinned = []
             self.lib.b200msdf_destroy(self.h)
             self.h = C.c_void_p()
 
@@ -112,8 +138,9 @@ class Context:
         except Exception:
             pass
 
-    def set_stream(self, cuda_stream):
-        _lib.check(self.lib.b200msdf_set_stream(self.h, C.c_void_p(cuda_stream)))
+    def set_stream(self, cuda_stream, own=False):
+        """Run on the caller's cudaStream_t (0 = the CUDA default stream, which is torch's default); own=True returns to the context's stream."""
+        _lib.check(self.lib.b200msdf_set_stream(self.h, C.c_void_p(cuda_stream), int(own)))
 
     def synchronize(self):
         _lib.check(self.lib.b200msdf_synchronize(self.h))
@@ -123,25 +150,14 @@ class Context:
         return int(self.lib.b200msdf_launch_count(self.h))
 
     def pinned(self, shape, dtype):
-        """numpy array backed by pinned host memory from b200msdf_host_alloc (kept alive by the returned array's base)."""
+        """numpy array backed by pinned host memory from b200msdf_host_alloc; freed when the context is closed."""
         dtype = np.dtype(dtype)
-        n = int(np.prod(shape)) * dtype.itemsize
+        count = int(np.prod(shape))
         ptr = C.c_void_p()
-        _lib.check(self.lib.b200msdf_host_alloc(C.byref(ptr), max(n, 1)))
-        buf = (C.c_uint8 * max(n, 1)).from_address(ptr.value)
-        lib = self.lib
-
-        class _Owner:
-            def __init__(self):
-                self.ptr, self.buf = ptr, buf
-
-            def __del__(self):
-                lib.b200msdf_host_free(self.ptr)
-        owner = _Owner()
-        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        arr._b200_owner = owner if False else None  # numpy arrays cannot take attributes; keep owner in registry instead
-        _PINNED_OWNERS[id(buf)] = owner
-        return arr
+        _lib.check(self.lib.b200msdf_host_alloc(C.byref(ptr), max(count * dtype.itemsize, 1)))
+        self._pinned.append(ptr)
+        buf = (C.c_uint8 * max(count * dtype.itemsize, 1)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
     # ---- reference-shaped single-shape calls ----------------------------------------------------------------------
     def generate(self, mode, output, shape: FlatShapes, transformation, config: MSDFGeneratorConfig = None, out_ydown=False,
@@ -160,9 +176,7 @@ class Context:
         config = config or MSDFGeneratorConfig()
         xf, per = _transforms(transformations)
         n = shapes.n_glyphs
-        bms = (_lib.Bitmap * max(n, 1))()
-        for g in range(n):
-            bms[g] = _bitmap(outputs[g], bool(out_ydown[g]) if out_ydown is not None else False)
+        bms = _bitmaps(outputs, n, out_ydown)
         s = _shapes_struct(shapes)
         cfg = config.c()
         _lib.check(self.lib.b200msdf_generate_batch(self.h, mode, C.byref(s), xf, per, bms, C.byref(cfg)))
@@ -172,9 +186,7 @@ class Context:
         config = config or MSDFGeneratorConfig()
         xf, per = _transforms(transformations)
         n = shapes.n_glyphs
-        bms = (_lib.Bitmap * max(n, 1))()
-        for g in range(n):
-            bms[g] = _bitmap(sdfs[g], bool(sdf_ydown[g]) if sdf_ydown is not None else False)
+        bms = _bitmaps(sdfs, n, sdf_ydown)
         s = _shapes_struct(shapes)
         cfg = config.c(ec_buffer)
         _lib.check(self.lib.b200msdf_error_correction(self.h, sdfs[0].shape[2], C.byref(s), xf, per, bms, C.byref(cfg)))
@@ -189,9 +201,6 @@ class Context:
     # ---- HBM-resident batches --------------------------------------------------------------------------------------
     def upload(self, mode, shapes: FlatShapes, transformations, dims, out_ydown=None):
         return Batch(self, mode, shapes, transformations, dims, out_ydown)
-
-
-_PINNED_OWNERS = {}
 
 
 class Batch:

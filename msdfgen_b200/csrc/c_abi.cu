@@ -243,9 +243,11 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
 }
 
 template <typename K>
-int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, int *grid) {
+int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, size_t dynSmem, int *grid) {
     int perSM = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, CTA_THREADS, 0));
+    if (dynSmem)
+        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dynSmem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, CTA_THREADS, dynSmem));
     if (perSM < 1) perSM = 1;
     long long g = (long long) perSM*ctx->numSMs;
     *grid = (int) (g < nTiles ? g : nTiles);
@@ -254,16 +256,16 @@ int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, int *grid) {
 }
 
 template <typename K>
-int launch_tiles(b200msdf_ctx *ctx, K kernel, KernelParams &P, int perThreadDoubles) {
+int launch_tiles(b200msdf_ctx *ctx, K kernel, KernelParams &P, int perThreadDoubles, size_t dynSmem = 0) {
     int grid = 1, rc;
-    if ((rc = grid_for(ctx, kernel, P.nTiles, &grid))) return rc;
+    if ((rc = grid_for(ctx, kernel, P.nTiles, dynSmem, &grid))) return rc;
     P.scratchStride = (size_t) grid*CTA_THREADS;
     if (perThreadDoubles > 0) {
         if ((rc = ctx->scratch.reserve(P.scratchStride*(size_t) perThreadDoubles*sizeof(double)))) return rc;
         P.scratch = ctx->scratch.as<double>();
     } else
         P.scratch = nullptr;
-    kernel<<<grid, CTA_THREADS, 0, ctx->stream>>>(P);
+    kernel<<<grid, CTA_THREADS, dynSmem, ctx->stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     ++ctx->launches;
     return 0;
@@ -287,9 +289,10 @@ int launch_k1(b200msdf_ctx *ctx, int mode, bool overlap, KernelParams &P, int ma
 
 int launch_k2(b200msdf_ctx *ctx, int N, bool overlap, KernelParams &P, int maxContours) {
     int scratch = (overlap && maxContours > B200_LOCAL_CONTOURS) ? maxContours : 0;
+    const size_t smem = K2_SMEM_BYTES;
     if (N == 3)
-        return overlap ? launch_tiles(ctx, k2_error_correction<3, true>, P, scratch) : launch_tiles(ctx, k2_error_correction<3, false>, P, scratch);
-    return overlap ? launch_tiles(ctx, k2_error_correction<4, true>, P, scratch) : launch_tiles(ctx, k2_error_correction<4, false>, P, scratch);
+        return overlap ? launch_tiles(ctx, k2_error_correction<3, true>, P, scratch, smem) : launch_tiles(ctx, k2_error_correction<3, false>, P, scratch, smem);
+    return overlap ? launch_tiles(ctx, k2_error_correction<4, true>, P, scratch, smem) : launch_tiles(ctx, k2_error_correction<4, false>, P, scratch, smem);
 }
 
 void fill_params(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cfg, KernelParams &P) {
@@ -476,10 +479,10 @@ void b200msdf_destroy(b200msdf_ctx *ctx) {
     delete ctx;
 }
 
-int b200msdf_set_stream(b200msdf_ctx *ctx, void *cuda_stream) {
+int b200msdf_set_stream(b200msdf_ctx *ctx, void *cuda_stream, int use_own) {
     if (!ctx)
         return fail(B200MSDF_ERR_ARG, "null context");
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own;
+    ctx->stream = use_own ? ctx->own : static_cast<cudaStream_t>(cuda_stream);
     return 0;
 }
 

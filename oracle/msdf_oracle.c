@@ -762,6 +762,10 @@ static void interpolate(float *out, const ec_ctx *e, v2 pos) {
         out[i] = mixf(mixf(TX(e, l, b)[i], TX(e, r, b)[i], lr), mixf(TX(e, l, t)[i], TX(e, r, t)[i], lr), bt);
 }
 
+/* test-only statistic: number of exact shape-distance evaluations performed by the error-correction pass */
+static long long g_exact_evals = 0;
+long long oracle_exact_eval_count(int reset) { long long v = g_exact_evals; if (reset) g_exact_evals = 0; return v; }
+
 static int cls_evaluate(const classifier *k, double t, float m, int flags) {   /* :47-49 and :59-82 */
     (void) m;
     if (!k->useShape)
@@ -770,6 +774,7 @@ static int cls_evaluate(const classifier *k, double t, float m, int flags) {   /
         if (flags&CLS_ARTIFACT)
             return 1;
         const ec_ctx *e = k->e;
+        ++g_exact_evals;
         v2 tVector = smul(t, k->direction);
         float oldMSD[4], newMSD[3];
         v2 sdfCoord = vadd(k->sdfCoord, tVector);

@@ -1,0 +1,19 @@
+"""Reader for tests/golden/golden_v1.npz (written by tests/golden/make_golden.py from the compiled reference)."""
+import json
+import os
+
+import numpy as np
+
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz")
+
+
+def load_cases():
+    z = np.load(PATH)
+    index = json.loads(bytes(z["index"]).decode())
+    cases = []
+    for i, meta in enumerate(index):
+        c = dict(meta)
+        for k in ("cbegin", "points", "orders", "colors", "xf", "out", "stencil"):
+            c[k] = z[f"c{i}_{k}"]
+        cases.append(c)
+    return cases

@@ -1,0 +1,62 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/msdfgen_b200.h declares,
+and refuses to compute without a GPU (no silent fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from msdfgen_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "msdfgen_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(b200msdf_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    assert sorted(_lib.EXPORTS) == declared
+
+
+def test_version_and_default_config():
+    lib = _lib.load()
+    assert lib.b200msdf_version() == 100
+    cfg = _lib.Config()
+    lib.b200msdf_default_config(C.byref(cfg))
+    # MSDFGeneratorConfig() defaults, /root/reference/core/generator-config.h:46,52,62
+    assert (cfg.overlap_support, cfg.ec_mode, cfg.ec_distance_check_mode) == (1, 2, 1)
+    assert cfg.min_deviation_ratio == cfg.min_improve_ratio == 1.11111111111111111
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.Transform) == 48
+    assert C.sizeof(_lib.Bitmap) == 24
+    assert C.sizeof(_lib.Shapes) == 64
+    assert C.sizeof(_lib.Config) == 40
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.b200msdf_create(0, C.byref(h))
+    assert rc == -2 and not h.value
+    assert b"no CPU fallback" in lib.b200msdf_last_error()
+    # compute entry points reject a null context instead of computing anything
+    assert lib.b200msdf_generate(None, 3, None, None, None, None) != 0
+
+
+def test_product_does_not_reference_the_oracle():
+    """The shipped library and package must not import, link or load anything under oracle/."""
+    pkg = os.path.join(ROOT, "msdfgen_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle/" not in text.replace("no oracle", "") or "never links" in text or f.endswith(".py") and "oracle" not in text.split('"""')[-1], (dirpath, f)
+                assert "libmsdf_oracle" not in text and "libmsdfgen_ref" not in text and "from oracle" not in text and "import oracle" not in text, (dirpath, f)
