@@ -141,6 +141,9 @@ int b200msdf_batch_upload(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *sh
                           b200msdf_batch **batch);
 /* Enqueues the whole path (contour windings -> distance field -> error correction) for the batch. */
 int b200msdf_batch_launch(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200msdf_config *config);
+/* Same, restricted to some stages (for per-kernel timing): bit 0 windings/prepare, bit 1 distance field, bit 2 error correction.
+ * Later stages read what earlier stages of a previous full launch left in HBM. */
+int b200msdf_batch_launch_stages(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200msdf_config *config, unsigned stages);
 float *b200msdf_batch_device_output(const b200msdf_batch *batch);      /* device pointer, valid until batch_free */
 uint8_t *b200msdf_batch_device_stencil(const b200msdf_batch *batch);   /* device pointer to per-texel EC flags (1 byte/texel) */
 size_t b200msdf_batch_output_floats(const b200msdf_batch *batch);      /* total floats incl. alignment padding */

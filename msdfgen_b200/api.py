@@ -221,6 +221,11 @@ class Batch:
         cfg = (config or MSDFGeneratorConfig()).c()
         _lib.check(self.ctx.lib.b200msdf_batch_launch(self.ctx.h, self.h, C.byref(cfg)))
 
+    def launch_stages(self, stages, config: MSDFGeneratorConfig = None):
+        """stages: bit 0 windings/prepare, bit 1 distance field, bit 2 error correction (per-kernel timing)."""
+        cfg = (config or MSDFGeneratorConfig()).c()
+        _lib.check(self.ctx.lib.b200msdf_batch_launch_stages(self.ctx.h, self.h, C.byref(cfg), stages))
+
     @property
     def output_floats(self):
         return int(self.ctx.lib.b200msdf_batch_output_floats(self.h))

@@ -338,7 +338,7 @@ int check_config(const b200msdf_config *cfg) {
     return 0;
 }
 
-int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cfg) {
+int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cfg, unsigned stages = 7u) {
     int rc = check_config(cfg);
     if (rc) return rc;
     if (b->nGlyphs == 0 || b->nTiles == 0) {
@@ -351,9 +351,15 @@ int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
     P.field = ec ? b->field.as<float>() : b->out.as<float>();
     P.out = b->out.as<float>();
     P.stencil = ec ? b->stencil.as<uint8_t>() : nullptr;
-    if ((rc = launch_prologue(ctx, b, P))) return rc;
-    if ((rc = launch_k1(ctx, b->mode, cfg->overlap_support != 0, P, b->maxContours))) return rc;
-    if (ec)
+    if (stages&1u)
+        if ((rc = launch_prologue(ctx, b, P))) return rc;
+    if (!(stages&1u)) {
+        // the tile counters are normally reset by the prologue kernel
+        CUDA_TRY(cudaMemsetAsync(P.counters, 0, 2*sizeof(int), ctx->stream));
+    }
+    if (stages&2u)
+        if ((rc = launch_k1(ctx, b->mode, cfg->overlap_support != 0, P, b->maxContours))) return rc;
+    if (ec && (stages&4u))
         if ((rc = launch_k2(ctx, b->N, cfg->overlap_support != 0, P, b->maxContours))) return rc;
     b->launched = true;
     b->ecRan = ec;
@@ -635,6 +641,14 @@ int b200msdf_batch_launch(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200ms
     if (!batch)
         return fail(B200MSDF_ERR_ARG, "null batch");
     return launch_batch(ctx, batch, config);
+}
+
+int b200msdf_batch_launch_stages(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200msdf_config *config, unsigned stages) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!batch)
+        return fail(B200MSDF_ERR_ARG, "null batch");
+    return launch_batch(ctx, batch, config, stages);
 }
 
 float *b200msdf_batch_device_output(const b200msdf_batch *batch) { return batch ? batch->out.as<float>() : nullptr; }

@@ -1,0 +1,118 @@
+// flat_c_api.cpp — extern "C" access to the host shape preparation for callers that keep shapes as flat arrays
+// (the Python package, bench.py): builds msdfgen::Shape objects from a flat batch, runs Shape::normalize() and an edge
+// colouring on every glyph, and flattens the result again.  Host-only (no device work); this is the batch-ingest step that
+// precedes b200msdf_generate_batch (SURVEY.md §8f "next" #1).
+#include "msdfgen.h"
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+using namespace msdfgen;
+
+namespace {
+
+void buildShape(Shape &shape, const uint32_t *cbegin, uint32_t c0, uint32_t c1, const double *points, const uint8_t *orders, const uint8_t *colors, bool yDown) {
+    shape.contours.clear();
+    shape.inverseYAxis = yDown;
+    for (uint32_t c = c0; c < c1; ++c) {
+        Contour &contour = shape.addContour();
+        for (uint32_t s = cbegin[c]; s < cbegin[c+1]; ++s) {
+            const double *p = points+8*size_t(s);
+            EdgeColor col = EdgeColor(colors ? colors[s] : 7);
+            switch (orders[s]) {
+                case 1: contour.addEdge(EdgeHolder(new LinearSegment(Point2(p[0], p[1]), Point2(p[2], p[3]), col))); break;
+                case 2: contour.addEdge(EdgeHolder(new QuadraticSegment(Point2(p[0], p[1]), Point2(p[2], p[3]), Point2(p[4], p[5]), col))); break;
+                default: contour.addEdge(EdgeHolder(new CubicSegment(Point2(p[0], p[1]), Point2(p[2], p[3]), Point2(p[4], p[5]), Point2(p[6], p[7]), col))); break;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+/// Pass 1 of 2: prepares every glyph and returns the totals needed to size the output arrays. The prepared shapes are kept
+/// in an opaque handle until b200host_prepare_fetch / b200host_prepare_free.
+struct b200host_prepared {
+    std::vector<Shape> shapes;
+};
+
+int b200host_prepare_begin(int nGlyphs, const uint32_t *gbegin, const uint32_t *cbegin, const double *points, const uint8_t *orders, const uint8_t *colors,
+                           const uint8_t *yDown, int doNormalize, int coloring, double angleThreshold, unsigned long long seed,
+                           b200host_prepared **handle, int *outContours, int *outSegments) {
+    b200host_prepared *h = new b200host_prepared;
+    h->shapes.resize((size_t) nGlyphs);
+    int nc = 0, ns = 0;
+    for (int g = 0; g < nGlyphs; ++g) {
+        Shape &shape = h->shapes[(size_t) g];
+        buildShape(shape, cbegin, gbegin[g], gbegin[g+1], points, orders, colors, yDown ? yDown[g] != 0 : false);
+        if (doNormalize)
+            shape.normalize();
+        if (coloring == 1)
+            edgeColoringSimple(shape, angleThreshold, seed);
+        else if (coloring == 2)
+            edgeColoringInkTrap(shape, angleThreshold, seed);
+        nc += (int) shape.contours.size();
+        ns += shape.edgeCount();
+    }
+    *handle = h;
+    *outContours = nc;
+    *outSegments = ns;
+    return 0;
+}
+
+int b200host_prepare_fetch(b200host_prepared *h, uint32_t *gbegin, uint32_t *cbegin, double *points, uint8_t *orders, uint8_t *colors) {
+    uint32_t c = 0, s = 0;
+    gbegin[0] = 0;
+    cbegin[0] = 0;
+    for (size_t g = 0; g < h->shapes.size(); ++g) {
+        const Shape &shape = h->shapes[g];
+        for (size_t ci = 0; ci < shape.contours.size(); ++ci) {
+            const std::vector<EdgeHolder> &edges = shape.contours[ci].edges;
+            for (size_t i = 0; i < edges.size(); ++i) {
+                const EdgeSegment *edge = edges[i];
+                int order = edge->type();
+                const Point2 *cp = edge->controlPoints();
+                for (int k = 0; k < 4; ++k) {
+                    points[8*size_t(s)+2*k] = k <= order ? cp[k].x : 0;
+                    points[8*size_t(s)+2*k+1] = k <= order ? cp[k].y : 0;
+                }
+                orders[s] = (uint8_t) order;
+                colors[s] = (uint8_t) edge->color;
+                ++s;
+            }
+            cbegin[++c] = s;
+        }
+        gbegin[g+1] = c;
+    }
+    return 0;
+}
+
+void b200host_prepare_free(b200host_prepared *h) { delete h; }
+
+/// Contour::winding() of every contour; Shape::validate() and Shape::getBounds() per glyph.
+int b200host_windings(int nContours, const uint32_t *cbegin, const double *points, const uint8_t *orders, int *out) {
+    Shape shape;
+    buildShape(shape, cbegin, 0, (uint32_t) nContours, points, orders, NULL, false);
+    for (int c = 0; c < nContours; ++c)
+        out[c] = shape.contours[(size_t) c].winding();
+    return 0;
+}
+
+int b200host_validate(int nContours, const uint32_t *cbegin, const double *points, const uint8_t *orders) {
+    Shape shape;
+    buildShape(shape, cbegin, 0, (uint32_t) nContours, points, orders, NULL, false);
+    return shape.validate() ? 1 : 0;
+}
+
+int b200host_bounds(int nContours, const uint32_t *cbegin, const double *points, const uint8_t *orders, double border, double miterLimit, int polarity, double *lbrt) {
+    Shape shape;
+    buildShape(shape, cbegin, 0, (uint32_t) nContours, points, orders, NULL, false);
+    Shape::Bounds b = shape.getBounds(border, miterLimit, polarity);
+    lbrt[0] = b.l; lbrt[1] = b.b; lbrt[2] = b.r; lbrt[3] = b.t;
+    return 0;
+}
+
+}

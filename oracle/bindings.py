@@ -67,8 +67,12 @@ def build(which=("port", "ref")):
         subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
 
 
-def ref_available(omp=False):
-    return os.path.exists(os.path.join(HERE, "_ref", "libmsdfgen_ref_omp.so" if omp else "libmsdfgen_ref.so"))
+_REF_LIBS = {"reference": "libmsdfgen_ref.so", "reference_omp": "libmsdfgen_ref_omp.so", "reference_gp": "libmsdfgen_ref_gp.so"}
+
+
+def ref_available(omp=False, kind=None):
+    kind = kind or ("reference_omp" if omp else "reference")
+    return os.path.exists(os.path.join(HERE, "_ref", _REF_LIBS[kind]))
 
 
 def port_available():
@@ -76,7 +80,8 @@ def port_available():
 
 
 class Oracle:
-    """One checker instance. kind: 'reference' | 'reference_omp' | 'port'."""
+    """One checker instance. kind: 'reference' (single thread) | 'reference_omp' (the reference's own row-parallel OpenMP
+    build) | 'reference_gp' (single-threaded reference core under the wrapper's outer OpenMP loop over glyphs) | 'port'."""
 
     def __init__(self, kind="reference"):
         self.kind = kind
@@ -87,7 +92,7 @@ class Oracle:
             self.lib = C.CDLL(path)
             self.pfx = "oracle_"
         else:
-            path = os.path.join(HERE, "_ref", "libmsdfgen_ref_omp.so" if kind == "reference_omp" else "libmsdfgen_ref.so")
+            path = os.path.join(HERE, "_ref", _REF_LIBS[kind])
             if not os.path.exists(path):
                 if not os.path.isdir(REF_DIR):
                     raise FileNotFoundError(f"{path} missing and {REF_DIR} absent: the reference oracle cannot be built here")

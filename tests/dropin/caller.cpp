@@ -1,0 +1,96 @@
+// caller.cpp — a msdfgen USER program, written only against the public msdfgen.h interface (README usage pattern,
+// /root/reference/README.md:114-142).  tests/test_dropin.py compiles this SAME file twice:
+//   * against the unmodified reference headers + core sources (-I/root/reference)          -> libcaller_ref.so
+//   * against msdfgen_b200/host/msdfgen.h + libmsdfgen_b200_host.so (the B200 backend)     -> libcaller_b200.so
+// and compares the outputs.  That it compiles unchanged against both is the drop-in claim; nothing here is B200-specific.
+#include "msdfgen.h"
+
+#include <cstdint>
+#include <cstring>
+
+using namespace msdfgen;
+
+static void buildShape(Shape &shape, int nContours, const uint32_t *cbegin, const double *pts, const uint8_t *orders, int yDown) {
+    for (int c = 0; c < nContours; ++c) {
+        Contour &contour = shape.addContour();
+        for (uint32_t s = cbegin[c]; s < cbegin[c+1]; ++s) {
+            const double *p = pts+8*s;
+            if (orders[s] == 1)
+                contour.addEdge(EdgeHolder(Point2(p[0], p[1]), Point2(p[2], p[3])));
+            else if (orders[s] == 2)
+                contour.addEdge(EdgeHolder(Point2(p[0], p[1]), Point2(p[2], p[3]), Point2(p[4], p[5])));
+            else
+                contour.addEdge(EdgeHolder(Point2(p[0], p[1]), Point2(p[2], p[3]), Point2(p[4], p[5]), Point2(p[6], p[7])));
+        }
+    }
+    if (yDown)
+        shape.setYAxisOrientation(Y_DOWNWARD);
+}
+
+static SDFTransformation autoframe(const Shape &shape, int w, int h, double pxRange) {
+    Shape::Bounds b = shape.getBounds();
+    double sx = w/(b.r-b.l)*.9, sy = h/(b.t-b.b)*.9;
+    double s = min(sx, sy);
+    Vector2 translate(-b.l+.5*(w/s-(b.r-b.l)), -b.b+.5*(h/s-(b.t-b.b)));
+    return SDFTransformation(Projection(Vector2(s), translate), Range(pxRange/s));
+}
+
+extern "C" {
+
+// README flow: normalize, colour, generateMSDF with the default config into an owning Bitmap.
+int caller_msdf(int nContours, const uint32_t *cbegin, const double *pts, const uint8_t *orders, int yDown, int w, int h, float *out) {
+    Shape shape;
+    buildShape(shape, nContours, cbegin, pts, orders, yDown);
+    if (!shape.validate())
+        return -1;
+    shape.normalize();
+    edgeColoringSimple(shape, 3.0);
+    Bitmap<float, 3> msdf(w, h);
+    generateMSDF(msdf, shape, autoframe(shape, w, h, 4.0));
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            memcpy(out+3*(size_t(w)*y+x), msdf(x, y), 3*sizeof(float));
+    return shape.edgeCount();
+}
+
+// Four generators into sections of one atlas-like buffer (row strides, Y_DOWNWARD section), plus the legacy overloads.
+// out: float[4][h][w][4] (unused channels stay at the fill value).
+int caller_all_modes(int nContours, const uint32_t *cbegin, const double *pts, const uint8_t *orders, int w, int h, int overlap, float *out) {
+    Shape shape;
+    buildShape(shape, nContours, cbegin, pts, orders, 0);
+    shape.normalize();
+    edgeColoringInkTrap(shape, 3.0, 3);
+    SDFTransformation t = autoframe(shape, w, h, 3.0);
+    Projection proj(t.projectVector(Vector2(1)), -t.unproject(Point2(0)));
+    Range range(3.0/t.projectVector(Vector2(1)).x);
+    size_t plane = size_t(w)*h*4;
+    // 1-channel results are written with a row stride of 4*w floats (every 4th float of the plane is a texel row start)
+    generateSDF(BitmapSection<float, 1>(out, w, h, 4*w), shape, t, GeneratorConfig(overlap != 0));
+    generatePSDF(BitmapSection<float, 1>(out+plane, w, h, 4*w, Y_DOWNWARD), shape, proj, range, GeneratorConfig(overlap != 0));
+    generateMSDF(BitmapSection<float, 3>(out+2*plane, w, h, 4*w), shape, range, t.projectVector(Vector2(1)), -t.unproject(Point2(0)), ErrorCorrectionConfig(), overlap != 0);
+    Bitmap<float, 4> mtsdf(w, h);
+    generateMTSDF(mtsdf, shape, t, MSDFGeneratorConfig(overlap != 0, ErrorCorrectionConfig(ErrorCorrectionConfig::EDGE_ONLY, ErrorCorrectionConfig::ALWAYS_CHECK_DISTANCE)));
+    memcpy(out+3*plane, (const float *) mtsdf, plane*sizeof(float));
+    return 0;
+}
+
+// Distance pass without correction, then the stand-alone correction entry points.
+int caller_error_correction(int nContours, const uint32_t *cbegin, const double *pts, const uint8_t *orders, int w, int h, float *out, uint8_t *stencil) {
+    Shape shape;
+    buildShape(shape, nContours, cbegin, pts, orders, 0);
+    shape.normalize();
+    edgeColoringSimple(shape, 3.0, 5);
+    SDFTransformation t = autoframe(shape, w, h, 4.0);
+    size_t plane = size_t(w)*h*3;
+    MSDFGeneratorConfig off(true, ErrorCorrectionConfig(ErrorCorrectionConfig::DISABLED));
+    for (int i = 0; i < 3; ++i)
+        generateMSDF(BitmapSection<float, 3>(out+i*plane, w, h), shape, t, off);
+    MSDFGeneratorConfig withBuffer(true, ErrorCorrectionConfig(ErrorCorrectionConfig::EDGE_PRIORITY, ErrorCorrectionConfig::CHECK_DISTANCE_AT_EDGE,
+        ErrorCorrectionConfig::defaultMinDeviationRatio, ErrorCorrectionConfig::defaultMinImproveRatio, stencil));
+    msdfErrorCorrection(BitmapSection<float, 3>(out, w, h), shape, t, withBuffer);
+    msdfFastDistanceErrorCorrection(BitmapSection<float, 3>(out+plane, w, h), t);
+    msdfFastEdgeErrorCorrection(BitmapSection<float, 3>(out+2*plane, w, h), t, 1.2);
+    return 0;
+}
+
+}

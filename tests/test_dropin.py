@@ -1,0 +1,92 @@
+"""Drop-in boundary test: one msdfgen USER program (tests/dropin/caller.cpp, public msdfgen.h API only) is compiled against
+the unmodified reference and against the B200 host mirror; the CPU leg checks that both compile and that the reference
+build agrees with the oracle port, the GPU leg checks the B200 build against it."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import compare, to_bytes
+from msdfgen_b200.synth import synth_glyph
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "dropin", "caller.cpp")
+OUT = os.path.join(ROOT, "tests", "dropin", "_build")
+REF = "/root/reference"
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def _build_ref():
+    if not os.path.isdir(REF):
+        pytest.skip("/root/reference is not present on this box")
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, "libcaller_ref.so")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(SRC):
+        core = sorted(os.path.join(REF, "core", f) for f in os.listdir(os.path.join(REF, "core")) if f.endswith(".cpp"))
+        subprocess.run([CXX, "-O2", "-ffp-contract=off", "-std=c++11", "-fPIC", "-shared", "-DMSDFGEN_PUBLIC=", "-DMSDFGEN_USE_CPP11",
+                        f"-I{REF}", "-o", lib, SRC] + core, check=True, capture_output=True)
+    return C.CDLL(lib)
+
+
+def _build_b200():
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, "libcaller_b200.so")
+    host = os.path.join(ROOT, "msdfgen_b200")
+    deps = [SRC, os.path.join(host, "host", "msdfgen.h"), os.path.join(host, "libmsdfgen_b200_host.so")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run([CXX, "-O2", "-ffp-contract=off", "-std=c++11", "-fPIC", "-shared", f"-I{host}/host", "-o", lib, SRC,
+                        f"-L{host}", "-lmsdfgen_b200_host", "-lmsdfgen_b200", f"-Wl,-rpath,{host}"], check=True, capture_output=True)
+    return C.CDLL(lib)
+
+
+def _args(g):
+    return (C.c_int(g.n_contours), g.cbegin.ctypes.data_as(C.POINTER(C.c_uint32)), g.points.ctypes.data_as(C.POINTER(C.c_double)),
+            g.orders.ctypes.data_as(C.POINTER(C.c_uint8)))
+
+
+def _run(lib, g, w=24, h=20):
+    res = {}
+    a = np.full((h, w, 3), np.nan, np.float32)
+    res["edges"] = lib.caller_msdf(*_args(g), C.c_int(0), C.c_int(w), C.c_int(h), a.ctypes.data_as(C.POINTER(C.c_float)))
+    res["msdf"] = a
+    b = np.full((4, h, w, 4), 7.0, np.float32)
+    assert lib.caller_all_modes(*_args(g), C.c_int(w), C.c_int(h), C.c_int(1), b.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    res["modes"] = b
+    c = np.full((3, h, w, 3), np.nan, np.float32)
+    st = np.zeros((h, w), np.uint8)
+    assert lib.caller_error_correction(*_args(g), C.c_int(w), C.c_int(h), c.ctypes.data_as(C.POINTER(C.c_float)), st.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
+    res["ec"], res["stencil"] = c, st
+    return res
+
+
+def test_caller_compiles_against_both_interfaces():
+    """Compile-time drop-in: the same user source builds against the reference headers and against the B200 mirror."""
+    _build_b200()
+    _build_ref()
+
+
+def test_reference_build_runs(ref):
+    lib = _build_ref()
+    r = _run(lib, synth_glyph(123, cubic_fraction=0.2))
+    assert r["edges"] > 0 and np.isfinite(r["msdf"]).all() and (r["stencil"] & 2).all()
+
+
+@pytest.mark.gpu
+def test_b200_build_matches_reference_build():
+    """Run-time drop-in on the GPU: same caller, two backends, same texels (falls back to a fixture when the reference
+    tree is not on the box)."""
+    b200 = _build_b200()
+    fixture = os.path.join(ROOT, "tests", "golden", "dropin_v1.npz")
+    z = np.load(fixture)
+    for i, seed in enumerate(z["seeds"]):
+        g = synth_glyph(int(seed), cubic_fraction=0.2)
+        mine = _run(b200, g)
+        assert mine["edges"] == int(z[f"edges{i}"])
+        for key in ("msdf", "modes", "ec"):
+            want = z[f"{key}{i}"]
+            bits, max_abs, over = compare(mine[key], want)
+            assert over == 0 and max_abs <= 1e-4, (key, seed, bits, max_abs)
+            assert np.array_equal(to_bytes(mine[key]), to_bytes(want))
+        assert np.array_equal(mine["stencil"], z[f"stencil{i}"])
