@@ -89,7 +89,9 @@ def _shapes_struct(s: FlatShapes):
 
 def _bitmap(a, ydown=False):
     h, w, n = a.shape
-    assert a.dtype == np.float32 and a.strides[2] == 4 and a.strides[1] == 4 * n and a.strides[0] % 4 == 0
+    assert a.dtype == np.float32
+    if a.size:
+        assert a.strides[2] == 4 and a.strides[1] == 4 * n and a.strides[0] % 4 == 0
     return _lib.Bitmap(a.ctypes.data_as(C.POINTER(C.c_float)), w, h, a.strides[0] // 4, int(ydown))
 
 
@@ -99,7 +101,8 @@ _BITMAP_DTYPE = np.dtype([("pixels", np.uint64), ("width", np.int32), ("height",
 def _bitmaps(outputs, n, ydown=None):
     """b200msdf_bitmap[n] for a packed float32[n,h,w,N] block (vectorised) or a list of per-glyph arrays."""
     if isinstance(outputs, np.ndarray) and outputs.ndim == 4:
-        assert outputs.dtype == np.float32 and outputs.shape[0] == n and outputs.strides[3] == 4 and outputs.strides[2] == 4 * outputs.shape[3]
+        assert outputs.dtype == np.float32 and outputs.shape[0] == n
+        assert outputs.size == 0 or (outputs.strides[3] == 4 and outputs.strides[2] == 4 * outputs.shape[3])
         rec = np.empty(max(n, 1), dtype=_BITMAP_DTYPE)
         rec["pixels"][:n] = outputs.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(outputs.strides[0])
         rec["width"], rec["height"], rec["row_stride"] = outputs.shape[2], outputs.shape[1], outputs.strides[1] // 4

@@ -2,7 +2,7 @@
 // No torch, no oracle, no CPU compute path: every entry point that produces texels does so with the sm_100a kernels in
 // kernels.cuh or fails.
 #include "../../include/msdfgen_b200.h"
-#include "kernels.cuh"
+#include "error_correction.cuh"
 
 #include <climits>
 #include <cstdarg>
@@ -71,6 +71,9 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// exact-distance candidate slots per 1024-texel tile (the default configuration produces about 7; ALWAYS_CHECK_DISTANCE about 230)
+const int EC_CANDIDATES_PER_TILE = 384;
+
 inline int channels_of(int mode) { return mode == B200MSDF_MSDF ? 3 : mode == B200MSDF_MTSDF ? 4 : 1; }
 
 }  // namespace
@@ -85,13 +88,13 @@ struct b200msdf_batch {
     bool hasColors = false;
     bool launched = false;
     bool ecRan = false;
-    DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, field, out, stencil;
+    DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, field, out, stencil, candidates, candCount;
     std::vector<GlyphDesc> hGlyphs;
     std::vector<TileDesc> hTiles;
     std::vector<int> hBig;
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
-        bigGlyphs.release(); bigRecs.release(); field.release(); out.release(); stencil.release();
+        bigGlyphs.release(); bigRecs.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release();
     }
 };
 
@@ -219,6 +222,8 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     if (b->N >= 3) {
         if ((rc = b->field.reserve(outFloats*4+64))) return rc;
         if ((rc = b->stencil.reserve(texels+64))) return rc;
+        if ((rc = b->candidates.reserve(sizeof(Candidate)*(size_t) EC_CANDIDATES_PER_TILE*(b->hTiles.size()+1)))) return rc;
+        if ((rc = b->candCount.reserve(sizeof(int)*(b->hTiles.size()+1)))) return rc;
     }
     if (b->nBig) {
         if ((rc = b->bigGlyphs.reserve(sizeof(int)*b->hBig.size()))) return rc;
@@ -243,11 +248,11 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
 }
 
 template <typename K>
-int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, size_t dynSmem, int *grid) {
+int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, size_t dynSmem, int threads, int *grid) {
     int perSM = 0;
     if (dynSmem)
         CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dynSmem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, CTA_THREADS, dynSmem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, dynSmem));
     if (perSM < 1) perSM = 1;
     long long g = (long long) perSM*ctx->numSMs;
     *grid = (int) (g < nTiles ? g : nTiles);
@@ -256,24 +261,24 @@ int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, size_t dynSmem, int *grid)
 }
 
 template <typename K>
-int launch_tiles(b200msdf_ctx *ctx, K kernel, KernelParams &P, int perThreadDoubles, size_t dynSmem = 0) {
+int launch_tiles(b200msdf_ctx *ctx, K kernel, KernelParams &P, int perThreadDoubles, size_t dynSmem = 0, int threads = CTA_THREADS) {
     int grid = 1, rc;
-    if ((rc = grid_for(ctx, kernel, P.nTiles, dynSmem, &grid))) return rc;
-    P.scratchStride = (size_t) grid*CTA_THREADS;
+    if ((rc = grid_for(ctx, kernel, P.nTiles, dynSmem, threads, &grid))) return rc;
+    P.scratchStride = (size_t) grid*threads;
     if (perThreadDoubles > 0) {
         if ((rc = ctx->scratch.reserve(P.scratchStride*(size_t) perThreadDoubles*sizeof(double)))) return rc;
         P.scratch = ctx->scratch.as<double>();
     } else
         P.scratch = nullptr;
-    kernel<<<grid, CTA_THREADS, dynSmem, ctx->stream>>>(P);
+    kernel<<<grid, threads, dynSmem, ctx->stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     ++ctx->launches;
     return 0;
 }
 
 int launch_k1(b200msdf_ctx *ctx, int mode, bool overlap, KernelParams &P, int maxContours) {
-    int nout = channels_of(mode);
-    int scratch = (overlap && maxContours > B200_LOCAL_CONTOURS) ? maxContours*nout : 0;
+    const int per[5] = { 0, StoreLayout<1>::PER_CONTOUR, StoreLayout<2>::PER_CONTOUR, StoreLayout<3>::PER_CONTOUR, StoreLayout<4>::PER_CONTOUR };
+    int scratch = (overlap && maxContours > B200_LOCAL_CONTOURS) ? maxContours*per[mode] : 0;
     switch (mode*2+(overlap ? 1 : 0)) {
         case 2: return launch_tiles(ctx, k1_distance_field<1, false>, P, scratch);
         case 3: return launch_tiles(ctx, k1_distance_field<1, true>, P, scratch);
@@ -287,12 +292,23 @@ int launch_k1(b200msdf_ctx *ctx, int mode, bool overlap, KernelParams &P, int ma
     return fail(B200MSDF_ERR_ARG, "bad mode");
 }
 
-int launch_k2(b200msdf_ctx *ctx, int N, bool overlap, KernelParams &P, int maxContours) {
-    int scratch = (overlap && maxContours > B200_LOCAL_CONTOURS) ? maxContours : 0;
-    const size_t smem = K2_SMEM_BYTES;
+// error correction = k2_classify (all texels) + k3_exact_distance (candidate verdicts; only when the configuration has a
+// shape-distance pass)
+int launch_k2(b200msdf_ctx *ctx, b200msdf_batch *b, int N, bool overlap, KernelParams &P, int maxContours) {
+    int rc;
+    P.candidates = b->candidates.as<Candidate>();
+    P.candCount = b->candCount.as<int>();
+    P.candCap = EC_CANDIDATES_PER_TILE;
+    bool shapePass = !P.shapeless && (P.ecDcm == 1 || P.ecDcm == 2);
+    if (shapePass)
+        CUDA_TRY(cudaMemsetAsync(P.candCount, 0, sizeof(int)*(size_t) P.nTiles, ctx->stream));
+    rc = N == 3 ? launch_tiles(ctx, k2_classify<3>, P, 0) : launch_tiles(ctx, k2_classify<4>, P, 0);
+    if (rc || !shapePass)
+        return rc;
+    int scratch = (overlap && maxContours > B200_LOCAL_CONTOURS) ? maxContours*StoreLayout<2>::PER_CONTOUR : 0;
     if (N == 3)
-        return overlap ? launch_tiles(ctx, k2_error_correction<3, true>, P, scratch, smem) : launch_tiles(ctx, k2_error_correction<3, false>, P, scratch, smem);
-    return overlap ? launch_tiles(ctx, k2_error_correction<4, true>, P, scratch, smem) : launch_tiles(ctx, k2_error_correction<4, false>, P, scratch, smem);
+        return overlap ? launch_tiles(ctx, k3_exact_distance<3, true>, P, scratch, 0, K3_THREADS) : launch_tiles(ctx, k3_exact_distance<3, false>, P, scratch, 0, K3_THREADS);
+    return overlap ? launch_tiles(ctx, k3_exact_distance<4, true>, P, scratch, 0, K3_THREADS) : launch_tiles(ctx, k3_exact_distance<4, false>, P, scratch, 0, K3_THREADS);
 }
 
 void fill_params(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cfg, KernelParams &P) {
@@ -355,12 +371,12 @@ int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
         if ((rc = launch_prologue(ctx, b, P))) return rc;
     if (!(stages&1u)) {
         // the tile counters are normally reset by the prologue kernel
-        CUDA_TRY(cudaMemsetAsync(P.counters, 0, 2*sizeof(int), ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(P.counters, 0, 3*sizeof(int), ctx->stream));
     }
     if (stages&2u)
         if ((rc = launch_k1(ctx, b->mode, cfg->overlap_support != 0, P, b->maxContours))) return rc;
     if (ec && (stages&4u))
-        if ((rc = launch_k2(ctx, b->N, cfg->overlap_support != 0, P, b->maxContours))) return rc;
+        if ((rc = launch_k2(ctx, b, b->N, cfg->overlap_support != 0, P, b->maxContours))) return rc;
     b->launched = true;
     b->ecRan = ec;
     return 0;
@@ -585,7 +601,7 @@ static int ec_common(b200msdf_ctx *ctx, int channels, const b200msdf_shapes *sha
     P.stencil = b->stencil.as<uint8_t>();
     P.shapeless = shapeless;
     if ((rc = launch_prologue(ctx, b, P))) return rc;
-    if ((rc = launch_k2(ctx, channels, config->overlap_support != 0, P, b->maxContours))) return rc;
+    if ((rc = launch_k2(ctx, b, channels, config->overlap_support != 0, P, b->maxContours))) return rc;
     if ((rc = download_to_bitmaps(ctx, b, b->out.as<float>(), sdfs))) return rc;
     if (!shapeless && config->ec_buffer && shapes->n_glyphs == 1 && b->texels) {
         CUDA_TRY(cudaMemcpyAsync(config->ec_buffer, b->stencil.p, b->texels, cudaMemcpyDeviceToHost, ctx->stream));

@@ -349,17 +349,32 @@ __device__ __forceinline__ Roots solve_cubic_normed(double a, double b, double c
 // ---------------------------------------------------------------------------------------------------------------------
 // EdgeSegment::signedDistance for the three segment types
 
-struct SDist { double d, dot, param; };
+// Result of EdgeSegment::signedDistance.  The reference also returns the curve parameter of the nearest point, but its
+// only consumers are range tests (param < 0, param > 1, 0 <= param <= 1, param < .5); those are decided exactly from the
+// numerator and denominator of the quotient (num/den < 0 <=> num < 0, num/den > 1 <=> num > den, num/den < .5 <=>
+// num < .5*den for den > 0 under round-to-nearest), so the fp64 division itself is never issued.
+struct SDist { double d, dot; int side; };   // side: 0 param in [0,1] (or NaN), 1 param < 0, 2 param > 1
+
+struct Param { double num, den; };
+__device__ __forceinline__ bool param_lt0(Param q) { return q.den > 0 ? q.num < 0 : (q.den == 0 && q.num != 0 && q.num < 0); }
+__device__ __forceinline__ bool param_gt1(Param q) { return q.den > 0 ? q.num > q.den : (q.den == 0 && q.num > 0); }
+__device__ __forceinline__ bool param_in01(Param q) { return q.den > 0 && q.num >= 0 && q.num <= q.den; }
+__device__ __forceinline__ bool param_lt_half(Param q) { return q.den > 0 ? q.num < .5*q.den : (q.den == 0 && q.num < 0); }
+__device__ __forceinline__ bool param_gt_half(Param q) { return q.den > 0 ? q.num > .5*q.den : (q.den == 0 && q.num > 0); }
+__device__ __forceinline__ int param_side(Param q) { return param_lt0(q) ? 1 : param_gt1(q) ? 2 : 0; }
 
 __device__ __forceinline__ SDist sd_linear(const SegRec &s, d2 p) {
     d2 aq = p-s.p0;
     d2 ab = mk(s.e[0], s.e[1]);
+    Param t;
+    t.num = dot(aq, ab);
+    t.den = s.e[2];
     SDist r;
-    r.param = dot(aq, ab)/s.e[2];
-    d2 ep = r.param > .5 ? s.p1 : s.p0;
+    r.side = param_side(t);
+    d2 ep = param_gt_half(t) ? s.p1 : s.p0;
     d2 eq = ep-p;
     double endpointDistance = len(eq);
-    if (r.param > 0 && r.param < 1) {
+    if (t.den > 0 && t.num > 0 && t.num < t.den) {    // param > 0 && param < 1
         double ortho = dot(mk(s.e[3], s.e[4]), aq);
         if (fabs(ortho) < endpointDistance) {
             r.d = ortho;
@@ -372,13 +387,13 @@ __device__ __forceinline__ SDist sd_linear(const SegRec &s, d2 p) {
     return r;
 }
 
-__device__ __forceinline__ void quad_root(const SegRec &s, d2 p, d2 qa, d2 ab, d2 br, double t, double &minDistance, double &param) {
+__device__ __forceinline__ void quad_root(d2 qa, d2 ab, d2 br, double t, double &minDistance, bool &interior) {
     if (t > 0 && t < 1) {
         d2 qe = qa+(2*t)*ab+(t*t)*br;
         double distance = len(qe);
         if (distance <= fabs(minDistance)) {
             minDistance = signed_by(cross(ab+t*br, qe), distance);
-            param = t;
+            interior = true;
         }
     }
 }
@@ -400,27 +415,34 @@ __device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p) {
     d2 epDir = mk(s.e[7], s.e[8]);
     double lenA = len(qa);
     double minDistance = signed_by(cross(epDir, qa), lenA);
-    double param = -dot(qa, epDir)/s.e[9];
+    Param param;
+    param.num = -dot(qa, epDir);
+    param.den = s.e[9];
     d2 qb = s.p2-p;
     double lenB = len(qb);
     if (lenB < fabs(minDistance)) {
         epDir = mk(s.e[10], s.e[11]);
         minDistance = signed_by(cross(epDir, qb), lenB);
-        param = dot(p-s.p1, epDir)/s.e[12];
+        param.num = dot(p-s.p1, epDir);
+        param.den = s.e[12];
     }
-    if (t.n > 0) quad_root(s, p, qa, ab, br, t.t0, minDistance, param);
-    if (t.n > 1) quad_root(s, p, qa, ab, br, t.t1, minDistance, param);
-    if (t.n > 2) quad_root(s, p, qa, ab, br, t.t2, minDistance, param);
+    bool interior = false;     // param became a root in (0,1)
+    if (t.n > 0) quad_root(qa, ab, br, t.t0, minDistance, interior);
+    if (t.n > 1) quad_root(qa, ab, br, t.t1, minDistance, interior);
+    if (t.n > 2) quad_root(qa, ab, br, t.t2, minDistance, interior);
 
     SDist r;
     r.d = minDistance;
-    r.param = param;
-    if (param >= 0 && param <= 1)
+    if (interior || param_in01(param)) {
         r.dot = 0;
-    else if (param < .5)
-        r.dot = fabs(dot(s.aDirNZ, normalize_known(qa, lenA)));
-    else
-        r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
+        r.side = 0;
+    } else {
+        r.side = param_side(param);
+        if (param_lt_half(param))
+            r.dot = fabs(dot(s.aDirNZ, normalize_known(qa, lenA)));
+        else
+            r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
+    }
     return r;
 }
 
@@ -433,14 +455,18 @@ __device__ __noinline__ SDist sd_cubic(const SegRec &s, d2 p) {
     d2 epDir = mk(s.e[7], s.e[8]);
     double lenA = len(qa);
     double minDistance = signed_by(cross(epDir, qa), lenA);
-    double param = -dot(qa, epDir)/s.e[9];
+    Param param;
+    param.num = -dot(qa, epDir);
+    param.den = s.e[9];
     d2 qb = s.p3-p;
     double lenB = len(qb);
     if (lenB < fabs(minDistance)) {
         epDir = mk(s.e[10], s.e[11]);
         minDistance = signed_by(cross(epDir, qb), lenB);
-        param = dot(epDir-qb, epDir)/s.e[12];
+        param.num = dot(epDir-qb, epDir);
+        param.den = s.e[12];
     }
+    bool interior = false;
     for (int i = 0; i <= 4; ++i) {      // MSDFGEN_CUBIC_SEARCH_STARTS
         double t = 1./4*i;
         d2 qe = qa+(3*t)*ab+(3*t*t)*br+(t*t*t)*as;
@@ -461,19 +487,22 @@ __device__ __noinline__ SDist sd_cubic(const SegRec &s, d2 p) {
             double distance = len(qe);
             if (distance < fabs(minDistance)) {
                 minDistance = signed_by(cross(d1, qe), distance);
-                param = t;
+                interior = true;    // param = t, which lies in (0,1)
             }
         }
     }
     SDist r;
     r.d = minDistance;
-    r.param = param;
-    if (param >= 0 && param <= 1)
+    if (interior || param_in01(param)) {
         r.dot = 0;
-    else if (param < .5)
-        r.dot = fabs(dot(s.aDirNZ, normalize_known(qa, lenA)));
-    else
-        r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
+        r.side = 0;
+    } else {
+        r.side = param_side(param);
+        if (param_lt_half(param))
+            r.dot = fabs(dot(s.aDirNZ, normalize_known(qa, lenA)));
+        else
+            r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
+    }
     return r;
 }
 
@@ -592,7 +621,7 @@ __device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, in
         return;
     }
     const int mask = MODE == 2 ? 1 : s.color;
-    int near = (recIndex<<2)|(r.param < 0 ? 1 : r.param > 1 ? 2 : 0);
+    int near = (recIndex<<2)|r.side;
     #pragma unroll
     for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
         if (mask&(1<<k))
@@ -633,106 +662,160 @@ __device__ __forceinline__ double resolve(const double *d) {
     return MODE >= 3 ? median3(d[0], d[1], d[2]) : d[0];
 }
 
-// Where the per-contour distances of the overlapping combiner live: a small per-thread array for typical glyphs, or a
-// slice of a global scratch buffer (stride = total threads) for shapes with many contours.
+// Per-contour results of the overlapping combiner, parked OUTSIDE the register file while the edges are walked: the
+// contour's selector state (so that the shape / inner / outer selectors can be merged afterwards exactly like the
+// reference does), its resolved distances and its winding.  A small per-thread local array serves typical glyphs; shapes
+// with many contours use a slice of a global scratch buffer (stride = total threads, so accesses coalesce).
 #define B200_LOCAL_CONTOURS 4
+template <int MODE> struct StoreLayout {
+    static const int CH = MODE == 1 ? 2 : 5;                                   // doubles per channel: d, dot [, neg, pos, near]
+    static const int STATE = ModeTraits<MODE>::NCH*CH;
+    static const int DIST = STATE;                                             // NOUT resolved distances
+    static const int WINDING = STATE+ModeTraits<MODE>::NOUT;
+    static const int PER_CONTOUR = WINDING+1;
+};
 struct ContourStore {
     double *base;
     size_t stride;
-    __device__ __forceinline__ double &at(int contour, int k, int nout) { return base[(size_t(contour)*nout+k)*stride]; }
+    int perContour;
+    __device__ __forceinline__ double &at(int contour, int k) { return base[(size_t(contour)*perContour+k)*stride]; }
 };
+
+template <int MODE>
+__device__ __forceinline__ void store_selector(ContourStore &st, int c, const Sel<MODE> &s) {
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NCH; ++k) {
+        const int o = k*StoreLayout<MODE>::CH;
+        st.at(c, o) = s.ch[k].d;
+        st.at(c, o+1) = s.ch[k].dot;
+        if (MODE != 1) {
+            st.at(c, o+2) = s.ch[k].neg;
+            st.at(c, o+3) = s.ch[k].pos;
+            st.at(c, o+4) = double(s.ch[k].near);
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void load_selector(ContourStore &st, int c, Sel<MODE> &s) {
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NCH; ++k) {
+        const int o = k*StoreLayout<MODE>::CH;
+        s.ch[k].d = st.at(c, o);
+        s.ch[k].dot = st.at(c, o+1);
+        if (MODE != 1) {
+            s.ch[k].neg = st.at(c, o+2);
+            s.ch[k].pos = st.at(c, o+3);
+            s.ch[k].near = int(st.at(c, o+4));
+        } else {
+            s.ch[k].neg = -DBL_MAX; s.ch[k].pos = DBL_MAX; s.ch[k].near = -1;
+        }
+    }
+}
 
 // ShapeDistanceFinder<Combiner<Selector>>::oneShotDistance at point p over the glyph's records [0, nRec).
 // recs is shared memory (small glyphs) or the global prepared buffer (big shapes); every thread of the CTA walks the same
 // record at the same time, so loads broadcast.  out gets NOUT raw (unmapped) fp64 distances.
 template <int MODE, bool OVERLAP>
-__device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, int nContours, d2 p, ContourStore store, double *out) {
+__device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, d2 p, ContourStore store, double *out) {
     const int NOUT = ModeTraits<MODE>::NOUT;
+    typedef StoreLayout<MODE> L;
     if (!OVERLAP) {
         Sel<MODE> sel;
         sel_init(sel);
         for (int j = 0; j < nRec; ++j)
             sel_add_edge<MODE>(sel, recs[j], j, p);
         sel_distance<MODE>(sel, recs, p, out);
-        return;
-    }
-    Sel<MODE> cur, shape, inner, outer;
-    sel_init(cur); sel_init(shape); sel_init(inner); sel_init(outer);
-    int ci = 0;
-    for (int j = 0; j < nRec; ++j) {
-        const SegRec &s = recs[j];
-        sel_add_edge<MODE>(cur, s, j, p);
-        if (s.flags&SEG_LAST_IN_CONTOUR) {
-            double cd[NOUT];
-            sel_distance<MODE>(cur, recs, p, cd);
-            #pragma unroll
-            for (int k = 0; k < NOUT; ++k)
-                store.at(ci, k, NOUT) = cd[k];
-            sel_merge<MODE>(shape, cur);
-            double rd = resolve<MODE>(cd);
-            int w = s.winding;
-            if (w > 0 && rd >= 0)
-                sel_merge<MODE>(inner, cur);
-            if (w < 0 && rd <= 0)
-                sel_merge<MODE>(outer, cur);
-            sel_init(cur);
-            ++ci;
-        }
-    }
-    double shapeD[NOUT], innerD[NOUT], outerD[NOUT], dist[NOUT];
-    sel_distance<MODE>(shape, recs, p, shapeD);
-    sel_distance<MODE>(inner, recs, p, innerD);
-    sel_distance<MODE>(outer, recs, p, outerD);
-    double innerScalar = resolve<MODE>(innerD), outerScalar = resolve<MODE>(outerD);
-    int winding;
-    if (innerScalar >= 0 && fabs(innerScalar) <= fabs(outerScalar)) {
-        #pragma unroll
-        for (int k = 0; k < NOUT; ++k) dist[k] = innerD[k];
-        winding = 1;
-    } else if (outerScalar <= 0 && fabs(outerScalar) < fabs(innerScalar)) {
-        #pragma unroll
-        for (int k = 0; k < NOUT; ++k) dist[k] = outerD[k];
-        winding = -1;
     } else {
-        #pragma unroll
-        for (int k = 0; k < NOUT; ++k) out[k] = shapeD[k];
-        return;
-    }
-    // The record that closes contour ci carries its winding; walk the closing records again (cheap: flags only).
-    // Pass 1: same-winding contours refine the inner/outer pick.  Pass 2: opposite/zero-winding contours may override it.
-    for (int pass = 0; pass < 2; ++pass) {
-        int c = 0;
-        for (int j = 0; j < nRec; ++j) {
-            if (!(recs[j].flags&SEG_LAST_IN_CONTOUR))
-                continue;
-            int w = recs[j].winding;
-            double cd[NOUT];
-            #pragma unroll
-            for (int k = 0; k < NOUT; ++k)
-                cd[k] = store.at(c, k, NOUT);
-            double rc = resolve<MODE>(cd), rdist = resolve<MODE>(dist);
-            bool take;
-            if (pass == 0) {
-                if (winding > 0)
-                    take = w > 0 && fabs(rc) < fabs(outerScalar) && rc > rdist;
-                else
-                    take = w < 0 && fabs(rc) < fabs(innerScalar) && rc < rdist;
-            } else
-                take = w != winding && rc*rdist >= 0 && fabs(rc) < fabs(rdist);
-            if (take) {
-                #pragma unroll
-                for (int k = 0; k < NOUT; ++k) dist[k] = cd[k];
+        // ---- walk the edges with ONE live selector; park each finished contour
+        int nc = 0;
+        {
+            Sel<MODE> cur;
+            sel_init(cur);
+            for (int j = 0; j < nRec; ++j) {
+                const SegRec &s = recs[j];
+                sel_add_edge<MODE>(cur, s, j, p);
+                if (s.flags&SEG_LAST_IN_CONTOUR) {
+                    double cd[NOUT];
+                    sel_distance<MODE>(cur, recs, p, cd);
+                    store_selector<MODE>(store, nc, cur);
+                    #pragma unroll
+                    for (int k = 0; k < NOUT; ++k)
+                        store.at(nc, L::DIST+k) = cd[k];
+                    store.at(nc, L::WINDING) = double(s.winding);
+                    sel_init(cur);
+                    ++nc;
+                }
             }
-            ++c;
         }
-    }
-    if (resolve<MODE>(dist) == resolve<MODE>(shapeD)) {
+        // ---- OverlappingContourCombiner::distance (contour-combiners.cpp:78-134)
+        double shapeD[NOUT], innerD[NOUT], outerD[NOUT], dist[NOUT];
+        {
+            Sel<MODE> shape, inner, outer;
+            sel_init(shape); sel_init(inner); sel_init(outer);
+            for (int c = 0; c < nc; ++c) {
+                Sel<MODE> sc;
+                load_selector<MODE>(store, c, sc);
+                double cd[NOUT];
+                #pragma unroll
+                for (int k = 0; k < NOUT; ++k)
+                    cd[k] = store.at(c, L::DIST+k);
+                double w = store.at(c, L::WINDING);
+                sel_merge<MODE>(shape, sc);
+                double rd = resolve<MODE>(cd);
+                if (w > 0 && rd >= 0)
+                    sel_merge<MODE>(inner, sc);
+                if (w < 0 && rd <= 0)
+                    sel_merge<MODE>(outer, sc);
+            }
+            sel_distance<MODE>(shape, recs, p, shapeD);
+            sel_distance<MODE>(inner, recs, p, innerD);
+            sel_distance<MODE>(outer, recs, p, outerD);
+        }
+        double innerScalar = resolve<MODE>(innerD), outerScalar = resolve<MODE>(outerD);
+        double winding;
+        if (innerScalar >= 0 && fabs(innerScalar) <= fabs(outerScalar)) {
+            #pragma unroll
+            for (int k = 0; k < NOUT; ++k) dist[k] = innerD[k];
+            winding = 1;
+        } else if (outerScalar <= 0 && fabs(outerScalar) < fabs(innerScalar)) {
+            #pragma unroll
+            for (int k = 0; k < NOUT; ++k) dist[k] = outerD[k];
+            winding = -1;
+        } else {
+            #pragma unroll
+            for (int k = 0; k < NOUT; ++k) out[k] = shapeD[k];
+            return;
+        }
+        // Pass 0: same-winding contours refine the inner/outer pick.  Pass 1: the others may override it.
+        for (int pass = 0; pass < 2; ++pass)
+            for (int c = 0; c < nc; ++c) {
+                double w = store.at(c, L::WINDING);
+                double cd[NOUT];
+                #pragma unroll
+                for (int k = 0; k < NOUT; ++k)
+                    cd[k] = store.at(c, L::DIST+k);
+                double rc = resolve<MODE>(cd), rdist = resolve<MODE>(dist);
+                bool take;
+                if (pass == 0) {
+                    if (winding > 0)
+                        take = w > 0 && fabs(rc) < fabs(outerScalar) && rc > rdist;
+                    else
+                        take = w < 0 && fabs(rc) < fabs(innerScalar) && rc < rdist;
+                } else
+                    take = w != winding && rc*rdist >= 0 && fabs(rc) < fabs(rdist);
+                if (take) {
+                    #pragma unroll
+                    for (int k = 0; k < NOUT; ++k) dist[k] = cd[k];
+                }
+            }
+        if (resolve<MODE>(dist) == resolve<MODE>(shapeD)) {
+            #pragma unroll
+            for (int k = 0; k < NOUT; ++k) dist[k] = shapeD[k];
+        }
         #pragma unroll
-        for (int k = 0; k < NOUT; ++k) dist[k] = shapeD[k];
+        for (int k = 0; k < NOUT; ++k) out[k] = dist[k];
     }
-    #pragma unroll
-    for (int k = 0; k < NOUT; ++k) out[k] = dist[k];
-    (void) nContours;
 }
 
 }  // namespace b200

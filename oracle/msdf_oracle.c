@@ -764,7 +764,9 @@ static void interpolate(float *out, const ec_ctx *e, v2 pos) {
 
 /* test-only statistic: number of exact shape-distance evaluations performed by the error-correction pass */
 static long long g_exact_evals = 0;
+static int g_stat_no_short_circuit = 0;   /* test-only: walk every neighbour test instead of stopping at the first hit (same flags) */
 long long oracle_exact_eval_count(int reset) { long long v = g_exact_evals; if (reset) g_exact_evals = 0; return v; }
+void oracle_stat_no_short_circuit(int on) { g_stat_no_short_circuit = on; }
 
 static int cls_evaluate(const classifier *k, double t, float m, int flags) {   /* :47-49 and :59-82 */
     (void) m;
@@ -887,8 +889,8 @@ static void ec_find_errors(ec_ctx *e, int useShape) {
             const float *l = x > 0 ? TX(e, x-1, y) : NULL, *b = y > 0 ? TX(e, x, y-1) : NULL;
             const float *r = x < w-1 ? TX(e, x+1, y) : NULL, *t = y < h-1 ? TX(e, x, y+1) : NULL;
             int err = 0;
-#define LIN(cond, nb, dx, dy, sp) if (!err && (cond)) { k.direction = V(dx, dy); k.span = sp; err = has_linear_artifact(&k, cm, c, nb); }
-#define DIA(cond, n1, n2, nd, dx, dy) if (!err && (cond)) { k.direction = V(dx, dy); k.span = dSpan; err = has_diagonal_artifact(&k, cm, c, n1, n2, nd); }
+#define LIN(cond, nb, dx, dy, sp) if ((!err || g_stat_no_short_circuit) && (cond)) { k.direction = V(dx, dy); k.span = sp; err |= has_linear_artifact(&k, cm, c, nb); }
+#define DIA(cond, n1, n2, nd, dx, dy) if ((!err || g_stat_no_short_circuit) && (cond)) { k.direction = V(dx, dy); k.span = dSpan; err |= has_diagonal_artifact(&k, cm, c, n1, n2, nd); }
             LIN(x > 0, l, -1, 0, hSpan)
             LIN(y > 0, b, 0, -1, vSpan)
             LIN(x < w-1, r, +1, 0, hSpan)

@@ -1,0 +1,216 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the committed
+golden vectors of the compiled reference, the C restatement, and — at BASELINE.json's full sizes — size-independent
+properties.  Bar (north_star): |delta| <= 1e-4 on every float and identical bytes after pixelFloatToByte; in practice the
+fp64 device path is bit-identical, so the tests also count differing float bit patterns and keep that count at zero
+wherever no transcendental is involved (it is reported, not asserted, elsewhere)."""
+import numpy as np
+import pytest
+
+from golden_io import load_cases
+from oracle.bindings import Config
+from util import compare, to_bytes
+
+from msdfgen_b200 import api, prep
+from msdfgen_b200.flat import FlatShapes
+from msdfgen_b200.synth import synth_atlas, synth_glyph, synth_big_shape, glyph_transform
+
+pytestmark = pytest.mark.gpu
+
+CASES = load_cases()
+MODE = {"sdf": api.SDF, "psdf": api.PSDF, "msdf": api.MSDF, "mtsdf": api.MTSDF}
+TOL = 1e-4
+
+
+def _cfg(c):
+    return api.MSDFGeneratorConfig(overlapSupport=c["overlap"], errorCorrection=api.ErrorCorrectionConfig(
+        mode=c["ec_mode"], distanceCheckMode=c["ec_dcm"], minDeviationRatio=c["min_dev"], minImproveRatio=c["min_imp"]))
+
+
+def _ocfg(cfg: api.MSDFGeneratorConfig):
+    e = cfg.errorCorrection
+    return Config(overlap=cfg.overlapSupport, ec_mode=e.mode, ec_dcm=e.distanceCheckMode, min_deviation_ratio=e.minDeviationRatio,
+                  min_improve_ratio=e.minImproveRatio)
+
+
+def assert_parity(got, want, what=""):
+    bits, max_abs, over = compare(got, want)
+    assert over == 0 and max_abs <= TOL, f"{what}: {over} texels over {TOL}, max |delta| {max_abs}, {bits} differing floats"
+    assert np.array_equal(to_bytes(got), to_bytes(want)), f"{what}: 8-bit quantisation differs"
+    return bits
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_vectors(ctx, case):
+    """generate{SDF,PSDF,MSDF,MTSDF} through b200msdf_generate vs the reference's own output, incl. the EC stencil."""
+    mode = MODE[case["mode"]]
+    shape = FlatShapes.single(case["cbegin"], case["points"], case["orders"], case["colors"], ydown=case["shape_ydown"])
+    out = np.full((case["h"], case["w"], api.CHANNELS[mode]), np.nan, np.float32)
+    st = np.full((case["h"], case["w"]), 255, np.uint8)
+    ec = mode >= api.MSDF and case["ec_mode"] != 0
+    ctx.generate(mode, out, shape, case["xf"], _cfg(case), out_ydown=case["out_ydown"], ec_buffer=st if ec else None)
+    assert_parity(out, case["out"], case["name"])
+    if ec:
+        assert np.array_equal(st, case["stencil"]), f"{case['name']}: stencil differs in {(st != case['stencil']).sum()} texels"
+
+
+def test_batch_equals_single_calls_and_port(ctx, port):
+    """A mixed batch (different sizes, orientations, per-glyph transforms, strided / flipped outputs) through
+    b200msdf_generate_batch equals per-glyph calls and the oracle."""
+    atlas = prep.prepare(synth_atlas(24, seed=4100, cubic_fraction=0.15))
+    rng = np.random.default_rng(1)
+    sizes = [(int(rng.integers(9, 40)), int(rng.integers(9, 40))) for _ in range(atlas.n_glyphs)]
+    xfs = np.array([[w * rng.uniform(0.8, 1.1), h * rng.uniform(0.8, 1.1), rng.uniform(-0.05, 0.1), rng.uniform(-0.05, 0.1), -2.0 / w, 2.5 / w] for w, h in sizes])
+    ydown = rng.integers(0, 2, atlas.n_glyphs)
+    atlas.ydown[:] = rng.integers(0, 2, atlas.n_glyphs)
+    for mode_name, mode in MODE.items():
+        n = api.CHANNELS[mode]
+        # outputs live inside one big "atlas page" with padding => non-packed row strides
+        page = np.full((atlas.n_glyphs, 48, 48 * n + 5), np.nan, np.float32)
+        outs = [page[g, 3:3 + h, 2:2 + w * n].reshape(h, w, n) for g, (w, h) in enumerate(sizes)]
+        assert all(o.base is not None for o in outs)
+        ctx.generate_batch(mode, outs, atlas, xfs, out_ydown=ydown)
+        for g, (w, h) in enumerate(sizes):
+            cb, pts, od, cl, yd = atlas.glyph(g)
+            want = port.generate(mode_name, cb, pts, od, cl, xfs[g], w, h, shape_ydown=yd, out_ydown=bool(ydown[g]))
+            assert_parity(outs[g], want, f"{mode_name} glyph {g}")
+            single = np.empty((h, w, n), np.float32)
+            ctx.generate(mode, single, FlatShapes.single(cb, pts, od, cl, ydown=yd), xfs[g], out_ydown=bool(ydown[g]))
+            assert np.array_equal(single.view(np.uint32), outs[g].view(np.uint32))
+        assert np.isnan(page[:, :3]).all() and np.isnan(page[:, :, :2]).all()      # nothing written outside the sections
+
+
+def test_negative_row_stride(ctx, port):
+    g = prep.prepare(synth_glyph(77))
+    w = 20
+    buf = np.full((w, w, 3), np.nan, np.float32)
+    flipped = buf[::-1]          # BitmapSection with negative rowStride
+    ctx.generate(api.MSDF, flipped, g, glyph_transform(w))
+    cb, pts, od, cl, _ = g.glyph(0)
+    want = port.generate("msdf", cb, pts, od, cl, glyph_transform(w), w, w)
+    assert_parity(flipped, want, "negative stride")
+
+
+def test_error_correction_entry_points(ctx, port):
+    g = prep.prepare(synth_glyph(99, cubic_fraction=0.2))
+    cb, pts, od, cl, _ = g.glyph(0)
+    xf = glyph_transform(28)
+    raw = np.empty((28, 28, 3), np.float32)
+    ctx.generate(api.MSDF, raw, g, xf, api.MSDFGeneratorConfig(errorCorrection=api.ErrorCorrectionConfig(mode=api.EC_DISABLED)))
+    for n in (3, 4):
+        field = raw if n == 3 else np.concatenate([raw, raw[..., :1]], axis=2).copy()
+        for ecm in (1, 2, 3):
+            for dcm in (0, 1, 2):
+                cfg = api.MSDFGeneratorConfig(errorCorrection=api.ErrorCorrectionConfig(mode=ecm, distanceCheckMode=dcm))
+                want, wst = port.error_correction(field, cb, pts, od, cl, xf, _ocfg(cfg), want_stencil=True)
+                got = field.copy()
+                st = np.zeros((28, 28), np.uint8)
+                ctx.error_correction([got], g, xf, cfg, ec_buffer=st)
+                assert_parity(got, want, f"ec n={n} mode={ecm} dcm={dcm}")
+                assert np.array_equal(st, wst)
+        for edge in (False, True):
+            want = port.fast_error_correction(field, xf, edge, 1.2)
+            got = ctx.fast_error_correction(field.copy(), xf, edge, 1.2)
+            assert_parity(got, want, f"fast ec edge={edge}")
+
+
+def test_degenerate_inputs(ctx):
+    empty = FlatShapes.single(np.zeros(1, np.uint32), np.zeros((0, 8)), np.zeros(0, np.uint8))
+    for mode in (api.SDF, api.MSDF, api.MTSDF):
+        out = np.zeros((6, 5, api.CHANNELS[mode]), np.float32)
+        ctx.generate(mode, out, empty, glyph_transform(6))
+        assert np.all(np.isneginf(out)), "empty shape must give -inf texels like the reference"
+    # empty batch and zero-sized bitmaps are no-ops
+    none = FlatShapes(np.zeros(1, np.uint32), np.zeros(1, np.uint32), np.zeros((0, 8)), np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.uint8))
+    ctx.generate_batch(api.MSDF, np.zeros((0, 4, 4, 3), np.float32), none, glyph_transform(4))
+    ctx.generate(api.MSDF, np.zeros((0, 7, 3), np.float32), prep.prepare(synth_glyph(1)), glyph_transform(7))
+    # invalid arguments are reported, not computed
+    with pytest.raises(Exception):
+        ctx.generate(9, np.zeros((4, 4, 3), np.float32), empty, glyph_transform(4))
+
+
+def test_big_shape_many_contours(ctx, port):
+    """Shapes beyond the shared-memory record budget (global prepared records) and beyond the per-thread contour store
+    (global scratch): a 12-contour, 360-segment shape."""
+    big = prep.prepare(synth_big_shape(n_contours=12, segs_per_contour=30, seed=5))
+    cb, pts, od, cl, _ = big.glyph(0)
+    xf = glyph_transform(48, px_range=6.0)
+    for mode_name in ("sdf", "psdf", "msdf", "mtsdf"):
+        for ov in (True, False):
+            cfg = api.MSDFGeneratorConfig(overlapSupport=ov)
+            out = np.empty((48, 48, api.CHANNELS[MODE[mode_name]]), np.float32)
+            ctx.generate(MODE[mode_name], out, big, xf, cfg)
+            want = port.generate(mode_name, cb, pts, od, cl, xf, 48, 48, _ocfg(cfg))
+            assert_parity(out, want, f"big {mode_name} overlap={ov}")
+
+
+def test_resident_batch_equals_host_api(ctx):
+    atlas = prep.prepare(synth_atlas(64, seed=8800))
+    xf = glyph_transform(32)
+    host = np.empty((64, 32, 32, 4), np.float32)
+    ctx.generate_batch(api.MTSDF, host, atlas, xf)
+    b = ctx.upload(api.MTSDF, atlas, xf, [32, 32])
+    b.launch()
+    flat = b.download()
+    for g in range(64):
+        assert np.array_equal(b.glyph(flat, g).view(np.uint32), host[g].view(np.uint32))
+    b.free()
+
+
+def test_full_size_atlas_properties(ctx, port):
+    """BASELINE configs[1] at full size (4096 glyphs, msdf 32x32) — too much for the oracle, so: sampled glyphs against the
+    oracle, batch determinism, and structural properties that hold for every glyph."""
+    n, w = 4096, 32
+    atlas = prep.prepare(synth_atlas(n))
+    xf = glyph_transform(w)
+    msdf = np.empty((n, w, w, 3), np.float32)
+    ctx.generate_batch(api.MSDF, msdf, atlas, xf)
+    again = np.empty_like(msdf)
+    ctx.generate_batch(api.MSDF, again, atlas, xf)
+    assert np.array_equal(msdf.view(np.uint32), again.view(np.uint32)), "non-deterministic"
+    for g in list(range(0, n, 171)) + [n - 1]:
+        cb, pts, od, cl, _ = atlas.glyph(g)
+        assert_parity(msdf[g], port.generate("msdf", cb, pts, od, cl, xf, w, w), f"glyph {g}")
+    off = api.MSDFGeneratorConfig(errorCorrection=api.ErrorCorrectionConfig(mode=api.EC_DISABLED))
+    raw = np.empty((n, w, w, 3), np.float32)
+    mt = np.empty((n, w, w, 4), np.float32)
+    sdf = np.empty((n, w, w, 1), np.float32)
+    ctx.generate_batch(api.MSDF, raw, atlas, xf, off)
+    ctx.generate_batch(api.MTSDF, mt, atlas, xf, off)
+    ctx.generate_batch(api.SDF, sdf, atlas, xf)
+    # MTSDF = MSDF colour channels + the true distance in alpha (edge-selectors.cpp:252-260)
+    assert np.array_equal(mt[..., :3].view(np.uint32), raw.view(np.uint32))
+    # with the simple combiner the alpha channel is exactly the SDF (every edge is coloured); the overlapping combiner
+    # picks contours by the median of r,g,b for MTSDF and by the true distance for SDF, so there they may differ
+    simple_off = api.MSDFGeneratorConfig(overlapSupport=False, errorCorrection=api.ErrorCorrectionConfig(mode=api.EC_DISABLED))
+    mt_s, sdf_s = np.empty_like(mt), np.empty_like(sdf)
+    ctx.generate_batch(api.MTSDF, mt_s, atlas, xf, simple_off)
+    ctx.generate_batch(api.SDF, sdf_s, atlas, xf, simple_off)
+    assert np.array_equal(mt_s[..., 3:].view(np.uint32), sdf_s.view(np.uint32))
+    assert (mt[..., 3:] != sdf).mean() < 0.01
+    # error correction only ever replaces a texel's three channels by their median, and never changes that median
+    med = lambda a: np.sort(a, axis=-1)[..., 1]
+    changed = (msdf.view(np.uint32) != raw.view(np.uint32)).any(axis=-1)
+    assert np.array_equal(med(msdf), med(raw))
+    assert (msdf[changed] == med(raw)[changed][:, None]).all()
+    assert 0.005 < changed.mean() < 0.2
+    # the sign of the median is the inside/outside classification of the true distance
+    inside = sdf[..., 0] > 0.5
+    m = med(raw)
+    decided = np.abs(sdf[..., 0] - 0.5) > 0.02
+    assert ((m > 0.5) == inside)[decided].mean() > 0.995
+    # flipping the output orientation flips rows, nothing else
+    flipped = np.empty_like(raw[:256])
+    sub = atlas.slice(0, 256)
+    ctx.generate_batch(api.MSDF, flipped, sub, xf, off, out_ydown=np.ones(256, np.uint8))
+    assert np.array_equal(flipped[:, ::-1].view(np.uint32), raw[:256].view(np.uint32))
+
+
+def test_mtsdf64_config3_sample(ctx, port):
+    """BASELINE configs[2] (mtsdf 64x64 with error correction) on a sample of glyphs against the oracle."""
+    atlas = prep.prepare(synth_atlas(48, seed=0xB200 + 4096))
+    xf = glyph_transform(64)
+    out = np.empty((48, 64, 64, 4), np.float32)
+    ctx.generate_batch(api.MTSDF, out, atlas, xf)
+    for g in range(0, 48, 5):
+        cb, pts, od, cl, _ = atlas.glyph(g)
+        assert_parity(out[g], port.generate("mtsdf", cb, pts, od, cl, xf, 64, 64), f"mtsdf64 glyph {g}")
