@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmsdfgen_b200.so")
+# B200MSDF_LIB selects an alternative build of the SAME library (kernel A/B experiments); default is the in-tree build.
+LIB_PATH = os.environ.get("B200MSDF_LIB") or os.path.join(HERE, "libmsdfgen_b200.so")
 
 # Every symbol include/msdfgen_b200.h declares (checked by tests/test_abi.py without a GPU).
 EXPORTS = [

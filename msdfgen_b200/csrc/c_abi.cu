@@ -80,7 +80,7 @@ inline int channels_of(int mode) { return mode == B200MSDF_MSDF ? 3 : mode == B2
 
 struct b200msdf_batch {
     int mode = 0, N = 0;
-    int nGlyphs = 0, nContours = 0, nSegments = 0, nTiles = 0;
+    int nGlyphs = 0, nContours = 0, nSegments = 0, nTiles = 0, nSmallTiles = 0;
     int nBig = 0;
     size_t nBigRecs = 0;
     size_t outFloats = 0, texels = 0;
@@ -162,6 +162,7 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     b->hBig.clear();
     size_t outFloats = 0, texels = 0, bigRecs = 0;
     int maxContours = 0;
+    std::vector<TileDesc> bigTiles;
     for (int g = 0; g < s->n_glyphs; ++g) {
         GlyphDesc &d = b->hGlyphs[(size_t) g];
         const b200msdf_transform &t = xf[xfPerGlyph ? g : 0];
@@ -199,9 +200,11 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
             TileDesc td;
             td.glyph = (unsigned) g;
             td.pix0 = (unsigned) p0;
-            b->hTiles.push_back(td);
+            (d.recBase < 0 ? b->hTiles : bigTiles).push_back(td);
         }
     }
+    b->nSmallTiles = (int) b->hTiles.size();
+    b->hTiles.insert(b->hTiles.end(), bigTiles.begin(), bigTiles.end());
     b->outFloats = outFloats;
     b->texels = texels;
     b->maxContours = maxContours;
@@ -263,7 +266,9 @@ int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, size_t dynSmem, int thread
 template <typename K>
 int launch_tiles(b200msdf_ctx *ctx, K kernel, KernelParams &P, int perThreadDoubles, size_t dynSmem = 0, int threads = CTA_THREADS) {
     int grid = 1, rc;
-    if ((rc = grid_for(ctx, kernel, P.nTiles, dynSmem, threads, &grid))) return rc;
+    if (P.tileEnd <= P.tileBegin)
+        return 0;
+    if ((rc = grid_for(ctx, kernel, P.tileEnd-P.tileBegin, dynSmem, threads, &grid))) return rc;
     P.scratchStride = (size_t) grid*threads;
     if (perThreadDoubles > 0) {
         if ((rc = ctx->scratch.reserve(P.scratchStride*(size_t) perThreadDoubles*sizeof(double)))) return rc;
@@ -276,18 +281,31 @@ int launch_tiles(b200msdf_ctx *ctx, K kernel, KernelParams &P, int perThreadDoub
     return 0;
 }
 
+template <int MODE, bool OVERLAP>
+int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
+    int rc;
+    P.tileBegin = 0; P.tileEnd = P.nSmallTiles; P.counterIndex = 0;
+    if ((rc = launch_tiles(ctx, k1_distance_field<MODE, OVERLAP, false>, P, scratch))) return rc;
+    P.tileBegin = P.nSmallTiles; P.tileEnd = P.nTiles; P.counterIndex = 3;
+    if ((rc = launch_tiles(ctx, k1_distance_field<MODE, OVERLAP, true>, P, scratch))) return rc;
+    P.tileBegin = 0; P.tileEnd = P.nTiles; P.counterIndex = 0;
+    return 0;
+}
+
 int launch_k1(b200msdf_ctx *ctx, int mode, bool overlap, KernelParams &P, int maxContours) {
     const int per[5] = { 0, StoreLayout<1>::PER_CONTOUR, StoreLayout<2>::PER_CONTOUR, StoreLayout<3>::PER_CONTOUR, StoreLayout<4>::PER_CONTOUR };
+    if (mode < 1 || mode > 4)
+        return fail(B200MSDF_ERR_ARG, "bad mode");
     int scratch = (overlap && maxContours > B200_LOCAL_CONTOURS) ? maxContours*per[mode] : 0;
     switch (mode*2+(overlap ? 1 : 0)) {
-        case 2: return launch_tiles(ctx, k1_distance_field<1, false>, P, scratch);
-        case 3: return launch_tiles(ctx, k1_distance_field<1, true>, P, scratch);
-        case 4: return launch_tiles(ctx, k1_distance_field<2, false>, P, scratch);
-        case 5: return launch_tiles(ctx, k1_distance_field<2, true>, P, scratch);
-        case 6: return launch_tiles(ctx, k1_distance_field<3, false>, P, scratch);
-        case 7: return launch_tiles(ctx, k1_distance_field<3, true>, P, scratch);
-        case 8: return launch_tiles(ctx, k1_distance_field<4, false>, P, scratch);
-        case 9: return launch_tiles(ctx, k1_distance_field<4, true>, P, scratch);
+        case 2: return launch_k1_mode<1, false>(ctx, P, scratch);
+        case 3: return launch_k1_mode<1, true>(ctx, P, scratch);
+        case 4: return launch_k1_mode<2, false>(ctx, P, scratch);
+        case 5: return launch_k1_mode<2, true>(ctx, P, scratch);
+        case 6: return launch_k1_mode<3, false>(ctx, P, scratch);
+        case 7: return launch_k1_mode<3, true>(ctx, P, scratch);
+        case 8: return launch_k1_mode<4, false>(ctx, P, scratch);
+        case 9: return launch_k1_mode<4, true>(ctx, P, scratch);
     }
     return fail(B200MSDF_ERR_ARG, "bad mode");
 }
@@ -302,13 +320,25 @@ int launch_k2(b200msdf_ctx *ctx, b200msdf_batch *b, int N, bool overlap, KernelP
     bool shapePass = !P.shapeless && (P.ecDcm == 1 || P.ecDcm == 2);
     if (shapePass)
         CUDA_TRY(cudaMemsetAsync(P.candCount, 0, sizeof(int)*(size_t) P.nTiles, ctx->stream));
+    P.tileBegin = 0; P.tileEnd = P.nTiles; P.counterIndex = 1;
     rc = N == 3 ? launch_tiles(ctx, k2_classify<3>, P, 0) : launch_tiles(ctx, k2_classify<4>, P, 0);
     if (rc || !shapePass)
         return rc;
     int scratch = (overlap && maxContours > B200_LOCAL_CONTOURS) ? maxContours*StoreLayout<2>::PER_CONTOUR : 0;
-    if (N == 3)
-        return overlap ? launch_tiles(ctx, k3_exact_distance<3, true>, P, scratch, 0, K3_THREADS) : launch_tiles(ctx, k3_exact_distance<3, false>, P, scratch, 0, K3_THREADS);
-    return overlap ? launch_tiles(ctx, k3_exact_distance<4, true>, P, scratch, 0, K3_THREADS) : launch_tiles(ctx, k3_exact_distance<4, false>, P, scratch, 0, K3_THREADS);
+    for (int big = 0; big < 2 && !rc; ++big) {
+        P.tileBegin = big ? P.nSmallTiles : 0;
+        P.tileEnd = big ? P.nTiles : P.nSmallTiles;
+        P.counterIndex = big ? 4 : 2;
+        if (N == 3) {
+            if (overlap) rc = big ? launch_tiles(ctx, k3_exact_distance<3, true, true>, P, scratch, 0, K3_THREADS) : launch_tiles(ctx, k3_exact_distance<3, true, false>, P, scratch, 0, K3_THREADS);
+            else rc = big ? launch_tiles(ctx, k3_exact_distance<3, false, true>, P, scratch, 0, K3_THREADS) : launch_tiles(ctx, k3_exact_distance<3, false, false>, P, scratch, 0, K3_THREADS);
+        } else {
+            if (overlap) rc = big ? launch_tiles(ctx, k3_exact_distance<4, true, true>, P, scratch, 0, K3_THREADS) : launch_tiles(ctx, k3_exact_distance<4, true, false>, P, scratch, 0, K3_THREADS);
+            else rc = big ? launch_tiles(ctx, k3_exact_distance<4, false, true>, P, scratch, 0, K3_THREADS) : launch_tiles(ctx, k3_exact_distance<4, false, false>, P, scratch, 0, K3_THREADS);
+        }
+    }
+    P.tileBegin = 0; P.tileEnd = P.nTiles; P.counterIndex = 0;
+    return rc;
 }
 
 void fill_params(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cfg, KernelParams &P) {
@@ -321,6 +351,10 @@ void fill_params(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
     P.glyphs = b->glyphs.as<GlyphDesc>();
     P.tiles = b->tiles.as<TileDesc>();
     P.nTiles = b->nTiles;
+    P.nSmallTiles = b->nSmallTiles;
+    P.tileBegin = 0;
+    P.tileEnd = b->nTiles;
+    P.counterIndex = 0;
     P.nContours = b->nContours;
     P.bigRecs = b->bigRecs.as<SegRec>();
     P.counters = ctx->counters.as<int>();
@@ -371,7 +405,7 @@ int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
         if ((rc = launch_prologue(ctx, b, P))) return rc;
     if (!(stages&1u)) {
         // the tile counters are normally reset by the prologue kernel
-        CUDA_TRY(cudaMemsetAsync(P.counters, 0, 3*sizeof(int), ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(P.counters, 0, 8*sizeof(int), ctx->stream));
     }
     if (stages&2u)
         if ((rc = launch_k1(ctx, b->mode, cfg->overlap_support != 0, P, b->maxContours))) return rc;

@@ -353,6 +353,9 @@ __device__ __forceinline__ Roots solve_cubic_normed(double a, double b, double c
 // only consumers are range tests (param < 0, param > 1, 0 <= param <= 1, param < .5); those are decided exactly from the
 // numerator and denominator of the quotient (num/den < 0 <=> num < 0, num/den > 1 <=> num > den, num/den < .5 <=>
 // num < .5*den for den > 0 under round-to-nearest), so the fp64 division itself is never issued.
+// `dot` (the orthogonality measure that only breaks exact |distance| ties between edges meeting at a corner) is evaluated
+// only when the edge can still become some channel's minimum, i.e. |d| <= need (SignedDistance::operator<): two fp64
+// divisions saved for every other edge.  When it is skipped the returned value is never read.
 struct SDist { double d, dot; int side; };   // side: 0 param in [0,1] (or NaN), 1 param < 0, 2 param > 1
 
 struct Param { double num, den; };
@@ -363,7 +366,7 @@ __device__ __forceinline__ bool param_lt_half(Param q) { return q.den > 0 ? q.nu
 __device__ __forceinline__ bool param_gt_half(Param q) { return q.den > 0 ? q.num > .5*q.den : (q.den == 0 && q.num > 0); }
 __device__ __forceinline__ int param_side(Param q) { return param_lt0(q) ? 1 : param_gt1(q) ? 2 : 0; }
 
-__device__ __forceinline__ SDist sd_linear(const SegRec &s, d2 p) {
+__device__ __forceinline__ SDist sd_linear(const SegRec &s, d2 p, double need) {
     d2 aq = p-s.p0;
     d2 ab = mk(s.e[0], s.e[1]);
     Param t;
@@ -383,7 +386,7 @@ __device__ __forceinline__ SDist sd_linear(const SegRec &s, d2 p) {
         }
     }
     r.d = signed_by(cross(aq, ab), endpointDistance);
-    r.dot = fabs(dot(s.aDirNZ, normalize_known(eq, endpointDistance)));
+    r.dot = endpointDistance <= need ? fabs(dot(s.aDirNZ, normalize_known(eq, endpointDistance))) : 0.0;
     return r;
 }
 
@@ -398,7 +401,7 @@ __device__ __forceinline__ void quad_root(d2 qa, d2 ab, d2 br, double t, double 
     }
 }
 
-__device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p) {
+__device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need) {
     d2 qa = s.p0-p;
     d2 ab = mk(s.e[0], s.e[1]);
     d2 br = mk(s.e[2], s.e[3]);
@@ -433,20 +436,22 @@ __device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p) {
 
     SDist r;
     r.d = minDistance;
-    if (interior || param_in01(param)) {
-        r.dot = 0;
+    r.dot = 0;
+    if (interior || param_in01(param))
         r.side = 0;
-    } else {
+    else {
         r.side = param_side(param);
-        if (param_lt_half(param))
-            r.dot = fabs(dot(s.aDirNZ, normalize_known(qa, lenA)));
-        else
-            r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
+        if (fabs(minDistance) <= need) {
+            if (param_lt_half(param))
+                r.dot = fabs(dot(s.aDirNZ, normalize_known(qa, lenA)));
+            else
+                r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
+        }
     }
     return r;
 }
 
-__device__ __noinline__ SDist sd_cubic(const SegRec &s, d2 p) {
+__device__ __noinline__ SDist sd_cubic(const SegRec &s, d2 p, double need) {
     d2 qa = s.p0-p;
     d2 ab = mk(s.e[0], s.e[1]);
     d2 br = mk(s.e[2], s.e[3]);
@@ -493,26 +498,28 @@ __device__ __noinline__ SDist sd_cubic(const SegRec &s, d2 p) {
     }
     SDist r;
     r.d = minDistance;
-    if (interior || param_in01(param)) {
-        r.dot = 0;
+    r.dot = 0;
+    if (interior || param_in01(param))
         r.side = 0;
-    } else {
+    else {
         r.side = param_side(param);
-        if (param_lt_half(param))
-            r.dot = fabs(dot(s.aDirNZ, normalize_known(qa, lenA)));
-        else
-            r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
+        if (fabs(minDistance) <= need) {
+            if (param_lt_half(param))
+                r.dot = fabs(dot(s.aDirNZ, normalize_known(qa, lenA)));
+            else
+                r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
+        }
     }
     return r;
 }
 
-__device__ __forceinline__ SDist signed_distance(const SegRec &s, d2 p) {
+__device__ __forceinline__ SDist signed_distance(const SegRec &s, d2 p, double need) {
     // s.order is uniform across the CTA (every thread walks the same record), so this switch does not diverge
     if (s.order == 1)
-        return sd_linear(s, p);
+        return sd_linear(s, p, need);
     if (s.order == 2)
-        return sd_quadratic(s, p);
-    return sd_cubic(s, p);
+        return sd_quadratic(s, p, need);
+    return sd_cubic(s, p, need);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -615,17 +622,23 @@ __device__ __forceinline__ void sel_distance(const Sel<MODE> &s, const SegRec *r
 // {True,Perpendicular,Multi}DistanceSelector::addEdge with every edge relevant
 template <int MODE>
 __device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, int recIndex, d2 p) {
-    SDist r = signed_distance(s, p);
-    if (MODE == 1) {
-        if (sd_less(r.d, r.dot, sel.ch[0].d, sel.ch[0].dot)) { sel.ch[0].d = r.d; sel.ch[0].dot = r.dot; }
-        return;
-    }
-    const int mask = MODE == 2 ? 1 : s.color;
-    int near = (recIndex<<2)|r.side;
+    const int mask = (MODE == 1 || MODE == 2) ? 1 : s.color;
+    // the edge can only replace a channel's minimum if |d| <= that minimum (SignedDistance operator<)
+    double need = 0;
     #pragma unroll
     for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
         if (mask&(1<<k))
-            if (sd_less(r.d, r.dot, sel.ch[k].d, sel.ch[k].dot)) { sel.ch[k].d = r.d; sel.ch[k].dot = r.dot; sel.ch[k].near = near; }
+            need = fmax(need, fabs(sel.ch[k].d));
+    SDist r = signed_distance(s, p, need);
+    if (fabs(r.d) <= need) {
+        int near = (recIndex<<2)|r.side;
+        #pragma unroll
+        for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+            if (mask&(1<<k))
+                if (sd_less(r.d, r.dot, sel.ch[k].d, sel.ch[k].dot)) { sel.ch[k].d = r.d; sel.ch[k].dot = r.dot; sel.ch[k].near = near; }
+    }
+    if (MODE == 1)
+        return;
     d2 ap = p-s.p0;
     d2 bp = p-s.pEnd;
     double add = dot(ap, s.aBis);

@@ -411,12 +411,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k2_classify(KernelParams P) {
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            s_tile = atomicAdd(&P.counters[1], 1);
+            s_tile = P.tileBegin+atomicAdd(&P.counters[P.counterIndex], 1);
             s_chunk = 0;
         }
         __syncthreads();
         int tile = s_tile;
-        if (tile >= P.nTiles)
+        if (tile >= P.tileEnd)
             break;
         TileDesc td = P.tiles[tile];
         if ((int) td.glyph != stagedGlyph) {
@@ -556,20 +556,19 @@ __device__ __forceinline__ void patch_texel(const KernelParams &P, const GlyphDe
     *st = f;
 }
 
-template <int N, bool OVERLAP>
+template <int N, bool OVERLAP, bool BIG>
 __global__ void __launch_bounds__(K3_THREADS) k3_exact_distance(KernelParams P) {
-    __shared__ SegRec s_recs[SMEM_RECORDS];
+    __shared__ SegRec s_recs[BIG ? 1 : SMEM_RECORDS];
     __shared__ GlyphDesc s_g;
     double localStore[B200_LOCAL_CONTOURS*StoreLayout<2>::PER_CONTOUR];
     const int lane = threadIdx.x;
     int stagedGlyph = -1;
-    const SegRec *recs = nullptr;
     for (;;) {
         int tile = 0;
         if (lane == 0)
-            tile = atomicAdd(&P.counters[2], 1);
+            tile = P.tileBegin+atomicAdd(&P.counters[P.counterIndex], 1);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= P.nTiles)
+        if (tile >= P.tileEnd)
             break;
         int pushed = P.candCount[tile];
         if (pushed == 0)
@@ -580,10 +579,12 @@ __global__ void __launch_bounds__(K3_THREADS) k3_exact_distance(KernelParams P) 
             if (lane == 0)
                 s_g = P.glyphs[td.glyph];
             __syncwarp();
-            recs = stage_glyph(P, s_g, s_recs);
+            if (!BIG)
+                stage_glyph(P, s_g, s_recs);
             stagedGlyph = (int) td.glyph;
             __syncwarp();
         }
+        const SegRec *recs = BIG ? P.bigRecs+s_g.recBase : s_recs;
         const int nRec = int(s_g.s1-s_g.s0);
         ContourStore store;
         store.perContour = StoreLayout<2>::PER_CONTOUR;

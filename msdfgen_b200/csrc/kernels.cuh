@@ -26,10 +26,13 @@ struct KernelParams {
     RawShapes raw;
     const GlyphDesc *glyphs;
     const TileDesc *tiles;
-    int nTiles;
+    int nTiles;                   // tiles [0, nSmallTiles) belong to glyphs staged in shared memory, the rest to big shapes
+    int nSmallTiles;
+    int tileBegin, tileEnd;       // tile range of this launch
+    int counterIndex;             // which counter this launch pulls tiles from
     int nContours;
     const SegRec *bigRecs;        // prepared records of big shapes
-    int *counters;                // [0] k1, [1] k2, [2] k3 tile counters
+    int *counters;                // tile counters: [0],[3] k1 small/big, [1] k2, [2],[4] k3 small/big
     struct Candidate *candidates; // k2 -> k3: per-tile slots of exact-distance checks, candCap per tile
     int *candCount;               // per-tile number of pushes (may exceed candCap: overflow texels carry EC_FLAG_RECHECK)
     int candCap;
@@ -49,9 +52,9 @@ struct KernelParams {
 __global__ void k0_windings(RawShapes raw, int nContours, int8_t *windings, int *counters) {
     int c = blockIdx.x*blockDim.x+threadIdx.x;
     if (c == 0) {
-        counters[0] = 0;
-        counters[1] = 0;
-        counters[2] = 0;
+        #pragma unroll
+        for (int i = 0; i < 8; ++i)
+            counters[i] = 0;
     }
     if (c < nContours)
         windings[c] = (int8_t) contour_winding(raw, (unsigned) c);
@@ -73,13 +76,11 @@ struct TileCursor {
     int glyph;
 };
 
-__device__ __forceinline__ const SegRec *stage_glyph(const KernelParams &P, const GlyphDesc &g, SegRec *smemRecs) {
-    if (g.recBase >= 0)
-        return P.bigRecs+g.recBase;
+// Small glyphs (<= SMEM_RECORDS segments): every thread of the CTA prepares records into shared memory.
+__device__ __forceinline__ void stage_glyph(const KernelParams &P, const GlyphDesc &g, SegRec *smemRecs) {
     unsigned n = g.s1-g.s0;
     for (unsigned j = threadIdx.x; j < n; j += blockDim.x)
         prepare_record(P.raw, g, j, smemRecs[j]);
-    return smemRecs;
 }
 
 // Coalesced write-back of nFloats staged floats to dst (16-byte aligned when aligned == true).
@@ -98,34 +99,37 @@ __device__ __forceinline__ void store_tile(float *dst, const float *staged, int 
     }
 }
 
-template <int MODE, bool OVERLAP>
+// BIG = false: tiles of glyphs whose records are prepared into shared memory by the CTA (the compiler sees a __shared__
+// array: LDS).  BIG = true: tiles of shapes whose records were prepared into the global buffer by k0_prepare_big.
+template <int MODE, bool OVERLAP, bool BIG>
 __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams P) {
     const int NOUT = ModeTraits<MODE>::NOUT;
-    __shared__ SegRec s_recs[SMEM_RECORDS];
+    __shared__ SegRec s_recs[BIG ? 1 : SMEM_RECORDS];
     __shared__ __align__(16) float s_out[CTA_THREADS*NOUT];
     __shared__ GlyphDesc s_g;
     __shared__ int s_tile;
 
     double localStore[OVERLAP ? B200_LOCAL_CONTOURS*StoreLayout<MODE>::PER_CONTOUR : 1];
     int stagedGlyph = -1;
-    const SegRec *recs = nullptr;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0)
-            s_tile = atomicAdd(&P.counters[0], 1);
+            s_tile = P.tileBegin+atomicAdd(&P.counters[P.counterIndex], 1);
         __syncthreads();
         int tile = s_tile;
-        if (tile >= P.nTiles)
+        if (tile >= P.tileEnd)
             break;
         TileDesc td = P.tiles[tile];
         if ((int) td.glyph != stagedGlyph) {
             if (threadIdx.x == 0)
                 s_g = P.glyphs[td.glyph];
             __syncthreads();
-            recs = stage_glyph(P, s_g, s_recs);
+            if (!BIG)
+                stage_glyph(P, s_g, s_recs);
             stagedGlyph = (int) td.glyph;
             __syncthreads();
         }
+        const SegRec *recs = BIG ? P.bigRecs+s_g.recBase : s_recs;
         const int w = s_g.w;
         const unsigned total = unsigned(w)*unsigned(s_g.h);
         const int nRec = int(s_g.s1-s_g.s0);
