@@ -80,6 +80,9 @@ struct __align__(16) SegRec {
     //              e10,11 = direction(1)  e12 = its sq. length  e13 = e5/e4
     //   cubic:     e0,1 = ab   e2,3 = br    e4,5 = as   e7..e12 as quadratic
     double e[14];
+    d2 bc;                 // bounding circle of the whole curve (centre, radius incl. safety margin): every point of the
+    double br;             // segment lies within br of bc — used only to SKIP work that provably cannot matter
+    double pad2;
     int order;             // 1, 2, 3
     int color;             // EdgeColor mask
     int flags;
@@ -236,6 +239,19 @@ __device__ inline void prepare_record(const RawShapes &rs, const GlyphDesc &g, u
         out.e[i] = 0;
     // p0 restored to the raw control point for the distance kernels (point(0) above only differs for non-finite input)
     d2 P0 = sc.p[0], P1 = sc.p[1], P2 = sc.p[2], P3 = sc.p[3];
+    {
+        // control-point hull: a Bezier curve lies inside the convex hull of its control points
+        double xmin = fmin(P0.x, P1.x), xmax = fmax(P0.x, P1.x), ymin = fmin(P0.y, P1.y), ymax = fmax(P0.y, P1.y);
+        if (sc.order >= 2) { xmin = fmin(xmin, P2.x); xmax = fmax(xmax, P2.x); ymin = fmin(ymin, P2.y); ymax = fmax(ymax, P2.y); }
+        if (sc.order >= 3) { xmin = fmin(xmin, P3.x); xmax = fmax(xmax, P3.x); ymin = fmin(ymin, P3.y); ymax = fmax(ymax, P3.y); }
+        d2 c = mk(.5*(xmin+xmax), .5*(ymin+ymax));
+        double r2 = fmax(dot(P0-c, P0-c), dot(P1-c, P1-c));
+        if (sc.order >= 2) r2 = fmax(r2, dot(P2-c, P2-c));
+        if (sc.order >= 3) r2 = fmax(r2, dot(P3-c, P3-c));
+        out.bc = c;
+        out.br = sqrt(r2)*(1+1e-9);
+        out.pad2 = 0;
+    }
     if (sc.order == 1) {
         d2 ab = P1-P0;
         out.e[0] = ab.x; out.e[1] = ab.y;
@@ -259,6 +275,7 @@ __device__ inline void prepare_record(const RawShapes &rs, const GlyphDesc &g, u
             if (a != 0) {
                 double bn = bq/a;
                 out.e[13] = bn;
+                out.p3.x = 1/a;     // quadratics do not use p3: reciprocal of the leading coefficient for the fast root path
                 if (fabs(bn) < 1e6)
                     flags |= SEG_CUBIC_NORMED;
             }
@@ -347,6 +364,70 @@ __device__ __forceinline__ Roots solve_cubic_normed(double a, double b, double c
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Fast roots of the foot-point cubic t^3 + A t^2 + B t + C = 0 (quadratic segments).
+//
+// The reference evaluates the closed form in fp64 (acos + 3 cos, or pow — equation-solver.cpp:34-61); on the GPU those
+// software transcendentals and the two normalising divisions are the largest single cost of the distance kernel.  The roots
+// are only used as curve parameters at which the squared distance is STATIONARY, so the distance obtained from a root
+// carries an error that is second order in the root's error: any t within ~1e-10 of the true root reproduces the
+// reference's distance to the last bit or two of fp64, far below the fp32 texel.  So: closed form in fp32 (hardware
+// rsqrt / cos approximations) for a ~1e-6 starting value, then Newton steps in fp64 on the cubic (reciprocal of the
+// derivative in fp32 — Newton is self-correcting) down to ~1e-14.  Only roots near [0,1] are polished; coefficient ranges
+// the fp32 stage cannot represent fall back to the exact path.  Compile with -DB200_EXACT_ROOTS=1 for the literal solver.
+#ifndef B200_EXACT_ROOTS
+#define B200_EXACT_ROOTS 0
+#endif
+
+__device__ __forceinline__ double cubic_polish(double t, double A, double B, double C) {
+    #pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double f = fma(fma(t+A, t, B), t, C);
+        double df = fma(fma(3.0, t, A+A), t, B);
+        float rdf = __frcp_rn(float(df));
+        // a vanishing derivative (double root) leaves t where it is: such roots are inflections of the distance, never its minimum
+        if (isfinite(rdf))
+            t = fma(-f, double(rdf), t);
+    }
+    return t;
+}
+
+__device__ __forceinline__ Roots solve_cubic_fast(double A, double B, double C, bool &ok) {
+    Roots x; x.t0 = x.t1 = x.t2 = 0; x.n = 0;
+    double a2 = A*A;
+    double q = 1/9.*(a2-3*B);
+    double r = 1/54.*(A*(2*a2-9*B)+27*C);
+    ok = fabs(q) < 1e12 && fabs(r) < 1e18;      // keep q^3, r^2 inside fp32 range
+    if (!ok)
+        return x;
+    float qf = float(q), rf = float(r);
+    double a3 = A*(1/3.);
+    double cand0, cand1 = 2, cand2 = 2;         // 2 = "no root" (outside the polishing window)
+    if (r*r < q*q*q) {
+        float sq = sqrtf(qf);
+        float t = rf/(qf*sq);
+        t = fminf(fmaxf(t, -1.f), 1.f);
+        float th = acosf(t);
+        float m = -2.f*sq;
+        cand0 = double(m*__cosf(th*(1/3.f)))-a3;
+        cand1 = double(m*__cosf((th+6.2831853f)*(1/3.f)))-a3;
+        cand2 = double(m*__cosf((th-6.2831853f)*(1/3.f)))-a3;
+    } else {
+        float disc = sqrtf(fmaxf(rf*rf-qf*qf*qf, 0.f));
+        float u = cbrtf(fabsf(rf)+disc);
+        u = rf < 0 ? u : -u;
+        float v = u == 0 ? 0.f : qf/u;
+        cand0 = double(u+v)-a3;
+        if (fabsf(u-v) <= 1e-3f*fabsf(u+v))
+            cand1 = double(-.5f*(u+v))-a3;      // (near-)double root
+    }
+    // polish what can end up inside (0,1)
+    if (cand0 > -.05 && cand0 < 1.05) { x.t0 = cubic_polish(cand0, A, B, C); x.n = 1; }
+    if (cand1 > -.05 && cand1 < 1.05) { double t = cubic_polish(cand1, A, B, C); if (x.n == 0) x.t0 = t; else x.t1 = t; ++x.n; }
+    if (cand2 > -.05 && cand2 < 1.05) { double t = cubic_polish(cand2, A, B, C); if (x.n == 0) x.t0 = t; else if (x.n == 1) x.t1 = t; else x.t2 = t; ++x.n; }
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // EdgeSegment::signedDistance for the three segment types
 
 // Result of EdgeSegment::signedDistance.  The reference also returns the curve parameter of the nearest point, but its
@@ -410,9 +491,16 @@ __device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need
     double c = s.e[6]+dot(qa, br);
     double d = dot(qa, ab);
     Roots t;
-    if (s.flags&SEG_CUBIC_NORMED)
+    if (s.flags&SEG_CUBIC_NORMED) {
+#if B200_EXACT_ROOTS
         t = solve_cubic_normed(s.e[13], c/a, d/a);
-    else
+#else
+        bool ok;
+        t = solve_cubic_fast(s.e[13], c*s.p3.x, d*s.p3.x, ok);
+        if (!ok)
+            t = solve_cubic_normed(s.e[13], c/a, d/a);
+#endif
+    } else
         t = solve_quadratic(b, c, d);
 
     d2 epDir = mk(s.e[7], s.e[8]);
@@ -619,55 +707,93 @@ __device__ __forceinline__ void sel_distance(const Sel<MODE> &s, const SegRec *r
     }
 }
 
-// {True,Perpendicular,Multi}DistanceSelector::addEdge with every edge relevant
+// {True,Perpendicular,Multi}DistanceSelector::addEdge (edge-selectors.cpp:19-29,129-160,174-227), cache-less.
+//
+// Exact culling.  cap[k] is an upper bound of channel k's FINAL minimum true distance within the selector's scope (the
+// distance from p to the start point of some edge of that channel).  With need = max over the edge's channels of
+// min(cap, current minimum), an edge whose bounding circle is farther than need from p has |d| > need, hence
+//   * it cannot become (or tie with) any of its channels' final minimum, so its signedDistance is not evaluated, and
+//   * a perpendicular candidate pd of it matters only if |pd| is below the channel's final |minimum| (a larger |pd| can
+//     at most become minNeg/minPos, which computeDistance then rejects in favour of the nearest edge's own distance); the
+//     reference adds pd iff |pd| < |d|, which for |pd| below the circle's lower bound is certainly true, and for every
+//     other |pd| is irrelevant by the previous sentence.
+// The result is bit-identical to evaluating every edge (the reference's EdgeCache prunes on the same principle, using
+// the previous pixel's distances instead of a bounding circle).
 template <int MODE>
-__device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, int recIndex, d2 p) {
+__device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, int recIndex, d2 p, const double *cap) {
     const int mask = (MODE == 1 || MODE == 2) ? 1 : s.color;
-    // the edge can only replace a channel's minimum if |d| <= that minimum (SignedDistance operator<)
     double need = 0;
     #pragma unroll
     for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
         if (mask&(1<<k))
-            need = fmax(need, fabs(sel.ch[k].d));
-    SDist r = signed_distance(s, p, need);
-    if (fabs(r.d) <= need) {
-        int near = (recIndex<<2)|r.side;
-        #pragma unroll
-        for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
-            if (mask&(1<<k))
-                if (sd_less(r.d, r.dot, sel.ch[k].d, sel.ch[k].dot)) { sel.ch[k].d = r.d; sel.ch[k].dot = r.dot; sel.ch[k].near = near; }
+            need = fmax(need, fmin(cap[k], fabs(sel.ch[k].d)));
+    d2 pc = p-s.bc;
+    const double dsq = dot(pc, pc);
+    const double reach = s.br+need;
+    const bool culled = dsq > reach*reach*(1+1e-9);
+    double rd = 0;
+    if (!culled) {
+        SDist r = signed_distance(s, p, need);
+        rd = r.d;
+        if (fabs(r.d) <= need) {
+            int near = (recIndex<<2)|r.side;
+            #pragma unroll
+            for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+                if (mask&(1<<k))
+                    if (sd_less(r.d, r.dot, sel.ch[k].d, sel.ch[k].dot)) { sel.ch[k].d = r.d; sel.ch[k].dot = r.dot; sel.ch[k].near = near; }
+        }
     }
     if (MODE == 1)
         return;
+    // Perpendicular candidates (getPerpendicularDistance + addEdgePerpendicularDistance).  A candidate can only influence
+    // a channel's result if |pd| <= that channel's final minimum true distance (see above), of which `need` is an upper
+    // bound for all channels of this edge — so the cheap |pd| test comes first and the domain tests only for survivors.
     d2 ap = p-s.p0;
-    d2 bp = p-s.pEnd;
-    double add = dot(ap, s.aBis);
-    double bdd = -dot(bp, s.bBis);
-    if (add > 0) {
+    double pdA = cross(ap, s.aDir);
+    if (fabs(pdA) <= need) {
         // getPerpendicularDistance(pd, ap, -aDir) followed by pd = -pd; the two negations cancel exactly
-        double ts = -dot(ap, s.aDir);
-        if (ts > 0) {
-            double pd = cross(ap, s.aDir);
-            if (fabs(pd) < fabs(r.d)) {
-                #pragma unroll
-                for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
-                    if (mask&(1<<k))
-                        chan_add_perp(sel.ch[k], pd);
-            }
+        double m = fabs(pdA)+s.br;
+        if (dot(ap, s.aBis) > 0 && -dot(ap, s.aDir) > 0 && (culled ? m*m*(1+1e-9) < dsq : fabs(pdA) < fabs(rd))) {
+            #pragma unroll
+            for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+                if (mask&(1<<k))
+                    chan_add_perp(sel.ch[k], pdA);
         }
     }
-    if (bdd > 0) {
-        double ts = dot(bp, s.bDir);
-        if (ts > 0) {
-            double pd = cross(bp, s.bDir);
-            if (fabs(pd) < fabs(r.d)) {
-                #pragma unroll
-                for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
-                    if (mask&(1<<k))
-                        chan_add_perp(sel.ch[k], pd);
-            }
+    d2 bp = p-s.pEnd;
+    double pdB = cross(bp, s.bDir);
+    if (fabs(pdB) <= need) {
+        double m = fabs(pdB)+s.br;
+        if (-dot(bp, s.bBis) > 0 && dot(bp, s.bDir) > 0 && (culled ? m*m*(1+1e-9) < dsq : fabs(pdB) < fabs(rd))) {
+            #pragma unroll
+            for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+                if (mask&(1<<k))
+                    chan_add_perp(sel.ch[k], pdB);
         }
     }
+}
+
+// cap[] for the records [j0, j1]: per channel, the distance from p to the nearest START POINT of an edge of that channel
+// (an upper bound of the channel's minimum true distance; the tiny inflation absorbs rounding differences between this
+// expression and the segment kernels').
+template <int MODE>
+__device__ __forceinline__ void distance_caps(const SegRec *recs, int j0, int j1, d2 p, double *cap) {
+    double capsq[ModeTraits<MODE>::NCH];
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+        capsq[k] = DBL_MAX;
+    for (int j = j0; j <= j1; ++j) {
+        const int mask = (MODE == 1 || MODE == 2) ? 1 : recs[j].color;
+        d2 v = p-recs[j].p0;
+        double q = dot(v, v);
+        #pragma unroll
+        for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+            if (mask&(1<<k))
+                capsq[k] = fmin(capsq[k], q);
+    }
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
+        cap[k] = sqrt(capsq[k])*(1+1e-12);
 }
 
 template <int MODE>
@@ -736,8 +862,10 @@ __device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, d2 
     if (!OVERLAP) {
         Sel<MODE> sel;
         sel_init(sel);
+        double cap[ModeTraits<MODE>::NCH];
+        distance_caps<MODE>(recs, 0, nRec-1, p, cap);
         for (int j = 0; j < nRec; ++j)
-            sel_add_edge<MODE>(sel, recs[j], j, p);
+            sel_add_edge<MODE>(sel, recs[j], j, p, cap);
         sel_distance<MODE>(sel, recs, p, out);
     } else {
         // ---- walk the edges with ONE live selector; park each finished contour
@@ -745,20 +873,26 @@ __device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, d2 
         {
             Sel<MODE> cur;
             sel_init(cur);
-            for (int j = 0; j < nRec; ++j) {
-                const SegRec &s = recs[j];
-                sel_add_edge<MODE>(cur, s, j, p);
-                if (s.flags&SEG_LAST_IN_CONTOUR) {
-                    double cd[NOUT];
-                    sel_distance<MODE>(cur, recs, p, cd);
-                    store_selector<MODE>(store, nc, cur);
-                    #pragma unroll
-                    for (int k = 0; k < NOUT; ++k)
-                        store.at(nc, L::DIST+k) = cd[k];
-                    store.at(nc, L::WINDING) = double(s.winding);
-                    sel_init(cur);
-                    ++nc;
-                }
+            int j0 = 0;
+            while (j0 < nRec) {
+                // the contour's records are [j0, j1]; its closing record carries SEG_LAST_IN_CONTOUR
+                int j1 = j0;
+                while (j1 < nRec-1 && !(recs[j1].flags&SEG_LAST_IN_CONTOUR))
+                    ++j1;
+                double cap[ModeTraits<MODE>::NCH];
+                distance_caps<MODE>(recs, j0, j1, p, cap);
+                for (int j = j0; j <= j1; ++j)
+                    sel_add_edge<MODE>(cur, recs[j], j, p, cap);
+                double cd[NOUT];
+                sel_distance<MODE>(cur, recs, p, cd);
+                store_selector<MODE>(store, nc, cur);
+                #pragma unroll
+                for (int k = 0; k < NOUT; ++k)
+                    store.at(nc, L::DIST+k) = cd[k];
+                store.at(nc, L::WINDING) = double(recs[j1].winding);
+                sel_init(cur);
+                ++nc;
+                j0 = j1+1;
             }
         }
         // ---- OverlappingContourCombiner::distance (contour-combiners.cpp:78-134)

@@ -13,7 +13,7 @@ import numpy as np
 from .flat import FlatShapes, WHITE
 
 
-def _ring(rng, cx, cy, radius, n, clockwise, cubic_fraction):
+def _ring(rng, cx, cy, radius, n, clockwise, cubic_fraction, linear_fraction=0.5):
     """One closed contour of n edges around (cx, cy). Returns (points[n,8], orders[n])."""
     ang = np.sort(rng.uniform(0.0, 2.0 * np.pi, n))
     # keep vertices from collapsing onto each other
@@ -32,7 +32,7 @@ def _ring(rng, cx, cy, radius, n, clockwise, cubic_fraction):
     bulge = rng.uniform(-0.3, 0.3, n)
     bulge2 = rng.uniform(-0.3, 0.3, n)
     for i in range(n):
-        if kind[i] < 0.5:
+        if kind[i] < linear_fraction:
             pts[i, 0:4] = (vx[i], vy[i], nx[i], ny[i])
         elif kind[i] < 1.0 - cubic_fraction:
             orders[i] = 2
@@ -46,7 +46,7 @@ def _ring(rng, cx, cy, radius, n, clockwise, cubic_fraction):
     return pts, orders
 
 
-def synth_glyph(seed, min_segments=8, max_segments=64, cubic_fraction=0.0, third_contour_prob=0.3):
+def synth_glyph(seed, min_segments=8, max_segments=64, cubic_fraction=0.0, third_contour_prob=0.3, linear_fraction=0.5):
     rng = np.random.Generator(np.random.PCG64(seed))
     n = int(rng.integers(min_segments, max_segments + 1))
     third = n >= 11 and rng.uniform() < third_contour_prob
@@ -58,11 +58,11 @@ def synth_glyph(seed, min_segments=8, max_segments=64, cubic_fraction=0.0, third
         n_outer = max(3, int(round(n * 0.58)))
         n_inner = max(3, n - n_outer)
         n_third = 0
-    parts = [_ring(rng, 0.5, 0.5, 0.45, n_outer, True, cubic_fraction),
-             _ring(rng, 0.5 + rng.uniform(-0.04, 0.04), 0.5 + rng.uniform(-0.04, 0.04), 0.22, n_inner, False, cubic_fraction)]
+    parts = [_ring(rng, 0.5, 0.5, 0.45, n_outer, True, cubic_fraction, linear_fraction),
+             _ring(rng, 0.5 + rng.uniform(-0.04, 0.04), 0.5 + rng.uniform(-0.04, 0.04), 0.22, n_inner, False, cubic_fraction, linear_fraction)]
     if third:
         a = rng.uniform(0, 2 * np.pi)
-        parts.append(_ring(rng, 0.5 + 0.33 * np.cos(a), 0.5 + 0.33 * np.sin(a), 0.16, n_third, True, cubic_fraction))
+        parts.append(_ring(rng, 0.5 + 0.33 * np.cos(a), 0.5 + 0.33 * np.sin(a), 0.16, n_third, True, cubic_fraction, linear_fraction))
     cbegin = np.cumsum([0] + [len(o) for _, o in parts]).astype(np.uint32)
     points = np.concatenate([p for p, _ in parts])
     orders = np.concatenate([o for _, o in parts])

@@ -214,3 +214,23 @@ def test_mtsdf64_config3_sample(ctx, port):
     for g in range(0, 48, 5):
         cb, pts, od, cl, _ = atlas.glyph(g)
         assert_parity(out[g], port.generate("mtsdf", cb, pts, od, cl, xf, 64, 64), f"mtsdf64 glyph {g}")
+
+
+def test_full_atlas_against_compiled_reference(ctx):
+    """BASELINE configs[1] and [2] at FULL size against the unmodified reference (possible because the compiled reference
+    runs glyph-parallel on the box's host cores in about a second): every one of the 12.6 M (msdf 32x32) and 67 M
+    (mtsdf 64x64, first 1024 glyphs) floats within 1e-4, identical bytes; the number of differing bit patterns is printed."""
+    from oracle import bindings
+    if not bindings.ref_available(kind="reference_gp"):
+        pytest.skip("compiled reference (oracle/_ref) did not travel to this box")
+    ref = bindings.Oracle("reference_gp")
+    n = 4096
+    atlas = prep.prepare(synth_atlas(n))
+    for mode_name, mode, w, count in (("msdf", api.MSDF, 32, n), ("mtsdf", api.MTSDF, 64, 1024), ("psdf", api.PSDF, 32, n)):
+        sub = atlas.slice(0, count)
+        xf = glyph_transform(w)
+        got = np.empty((count, w, w, api.CHANNELS[mode]), np.float32)
+        ctx.generate_batch(mode, got, sub, xf)
+        want, _ = ref.generate_batch(mode_name, sub.gbegin, sub.cbegin, sub.points, sub.orders, sub.colors, xf, w, w, glyph_parallel=True)
+        bits = assert_parity(got, want, f"full {mode_name} {w}x{w}")
+        print(f"[parity] {mode_name} {w}x{w} x{count}: {bits} of {got.size} floats differ in bit pattern, max |delta| {compare(got, want)[1]:.3g}")
