@@ -720,13 +720,15 @@ __device__ __forceinline__ void sel_distance(const Sel<MODE> &s, const SegRec *r
 // The result is bit-identical to evaluating every edge (the reference's EdgeCache prunes on the same principle, using
 // the previous pixel's distances instead of a bounding circle).
 template <int MODE>
-__device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, int recIndex, d2 p, const double *cap) {
+__device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, int recIndex, d2 p, double *lim) {
+    // lim[k] = min(cap[k], |current minimum of channel k|), kept up to date by this function; mask is uniform across the
+    // warp (every thread walks the same record), so the branches below do not diverge
     const int mask = (MODE == 1 || MODE == 2) ? 1 : s.color;
     double need = 0;
     #pragma unroll
     for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
         if (mask&(1<<k))
-            need = fmax(need, fmin(cap[k], fabs(sel.ch[k].d)));
+            need = dmax(need, lim[k]);
     d2 pc = p-s.bc;
     const double dsq = dot(pc, pc);
     const double reach = s.br+need;
@@ -740,7 +742,10 @@ __device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, in
             #pragma unroll
             for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
                 if (mask&(1<<k))
-                    if (sd_less(r.d, r.dot, sel.ch[k].d, sel.ch[k].dot)) { sel.ch[k].d = r.d; sel.ch[k].dot = r.dot; sel.ch[k].near = near; }
+                    if (sd_less(r.d, r.dot, sel.ch[k].d, sel.ch[k].dot)) {
+                        sel.ch[k].d = r.d; sel.ch[k].dot = r.dot; sel.ch[k].near = near;
+                        lim[k] = dmin(lim[k], fabs(r.d));
+                    }
         }
     }
     if (MODE == 1)
@@ -789,7 +794,7 @@ __device__ __forceinline__ void distance_caps(const SegRec *recs, int j0, int j1
         #pragma unroll
         for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
             if (mask&(1<<k))
-                capsq[k] = fmin(capsq[k], q);
+                capsq[k] = dmin(capsq[k], q);
     }
     #pragma unroll
     for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)

@@ -180,7 +180,7 @@ __device__ __forceinline__ float interp_median_quad(const float *a, const float 
 
 // hasLinearArtifactInner (:279-289)
 template <int N, int SINK, bool OVERLAP>
-__device__ __forceinline__ void linear_artifact_inner(const EcCtx<N> &e, TexelState &k, float am, float bm, const float *a, const float *b, float dA, float dB) {
+__device__ __noinline__ void linear_artifact_inner(const EcCtx<N> &e, TexelState &k, float am, float bm, const float *a, const float *b, float dA, float dB) {
     // t = dA/(dA-dB) lies strictly inside (0,1) only if dA and dB have strictly opposite signs; in every other case the
     // reference's range test (t > .01 && t < .99) fails as well, so the fp64 division is skipped without changing a result.
     if (!((dA > 0 && dB < 0) || (dA < 0 && dB > 0)))
@@ -196,7 +196,7 @@ __device__ __forceinline__ void linear_artifact_inner(const EcCtx<N> &e, TexelSt
 
 // hasDiagonalArtifactInner (:293-329)
 template <int N, int SINK, bool OVERLAP>
-__device__ __forceinline__ void diagonal_artifact_inner(const EcCtx<N> &e, TexelState &k, float am, float dm, const float *a, const float *l, const float *q,
+__device__ __noinline__ void diagonal_artifact_inner(const EcCtx<N> &e, TexelState &k, float am, float dm, const float *a, const float *l, const float *q,
                                                         float dA, float dBC, float dD, int ex0, int ex1) {
     // Two channels are equal where f(t) = qa t^2 + qb t + qc vanishes.  f has a zero strictly inside (0,1) only if it
     // changes sign between t = 0 and t = 1 or has its vertex inside (0,1); otherwise the reference's roots all fall outside
@@ -262,9 +262,13 @@ __device__ __forceinline__ void find_errors_texel(const EcCtx<N> &e, TexelState 
             continue;
         k.direction = mk(dx, dy);
         k.span = dx ? hSpan : vSpan;
-        linear_artifact_inner<N, SINK, OVERLAP>(e, k, am, bm, a, b, a[1]-a[0], b[1]-b[0]);
-        linear_artifact_inner<N, SINK, OVERLAP>(e, k, am, bm, a, b, a[2]-a[1], b[2]-b[1]);
-        linear_artifact_inner<N, SINK, OVERLAP>(e, k, am, bm, a, b, a[0]-a[2], b[0]-b[2]);
+        // channel pairs (g-r, b-g, r-b); the loop stays rolled to keep the kernel's instruction footprint small
+        #pragma unroll 1
+        for (int pr = 0; pr < 3; ++pr) {
+            float a0 = pr == 0 ? a[0] : pr == 1 ? a[1] : a[2], a1 = pr == 0 ? a[1] : pr == 1 ? a[2] : a[0];
+            float b0 = pr == 0 ? b[0] : pr == 1 ? b[1] : b[2], b1 = pr == 0 ? b[1] : pr == 1 ? b[2] : b[0];
+            linear_artifact_inner<N, SINK, OVERLAP>(e, k, am, bm, a, b, a1-a0, b1-b0);
+        }
     }
     // diagonally adjacent texels: hasDiagonalArtifact (:349-381) with b = horizontal, c = vertical neighbour
     k.span = dSpan;
@@ -287,9 +291,15 @@ __device__ __forceinline__ void find_errors_texel(const EcCtx<N> &e, TexelState 
         float abc[3] = { a[0]-b[0]-cc[0], a[1]-b[1]-cc[1], a[2]-b[2]-cc[2] };
         float l[3] = { -a[0]-abc[0], -a[1]-abc[1], -a[2]-abc[2] };
         float q[3] = { d[0]+abc[0], d[1]+abc[1], d[2]+abc[2] };
-        diagonal_artifact_inner<N, SINK, OVERLAP>(e, k, am, dm, a, l, q, a[1]-a[0], b[1]-b[0]+cc[1]-cc[0], d[1]-d[0], 0, 1);
-        diagonal_artifact_inner<N, SINK, OVERLAP>(e, k, am, dm, a, l, q, a[2]-a[1], b[2]-b[1]+cc[2]-cc[1], d[2]-d[1], 1, 2);
-        diagonal_artifact_inner<N, SINK, OVERLAP>(e, k, am, dm, a, l, q, a[0]-a[2], b[0]-b[2]+cc[0]-cc[2], d[0]-d[2], 2, 0);
+        #pragma unroll 1
+        for (int pr = 0; pr < 3; ++pr) {
+            const int i0 = pr, i1 = pr == 2 ? 0 : pr+1;
+            #define B200_PICK(v, i) ((i) == 0 ? v[0] : (i) == 1 ? v[1] : v[2])
+            float a0 = B200_PICK(a, i0), a1 = B200_PICK(a, i1), b0 = B200_PICK(b, i0), b1 = B200_PICK(b, i1);
+            float c0 = B200_PICK(cc, i0), c1 = B200_PICK(cc, i1), d0 = B200_PICK(d, i0), d1 = B200_PICK(d, i1);
+            #undef B200_PICK
+            diagonal_artifact_inner<N, SINK, OVERLAP>(e, k, am, dm, a, l, q, a1-a0, b1-b0+c1-c0, d1-d0, i0, i1);
+        }
     }
 }
 
@@ -396,7 +406,7 @@ __device__ __forceinline__ EcSpans ec_spans(const GlyphDesc &g, double minDeviat
 // independent and pull 32-texel chunks of the tile from a shared-memory counter (work per texel varies by orders of
 // magnitude between texels near an edge and the rest).
 template <int N>
-__global__ void __launch_bounds__(CTA_THREADS, 2) k2_classify(KernelParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
     __shared__ int2 s_corner[SMEM_RECORDS];
     __shared__ __align__(16) float s_out[EC_WARPS][32*4];
     __shared__ GlyphDesc s_g;
