@@ -139,6 +139,14 @@ int b200msdf_fast_error_correction(b200msdf_ctx *ctx, int channels, int edge, co
 int b200msdf_batch_upload(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
                           int transform_per_glyph, const int32_t *dims, int dims_per_glyph, const uint8_t *out_y_downward,
                           b200msdf_batch **batch);
+/* Same as b200msdf_batch_upload for REGIONS of larger images (tiling one huge shape across GPUs): origins = [2] shared or
+ * [2*n_glyphs] pixel coordinates (x0, y0) of each output block inside its full image; texel (x, y) of the block is evaluated at
+ * unproject(x0+x+.5, y0+y+.5), i.e. with full-image pixel coordinates, so tiles are bit-identical to the corresponding part of
+ * the untiled image.  Regions require the output orientation to equal the shape's and carry no error correction (a correction
+ * pass needs the neighbouring tiles' texels): mode must be SDF or PSDF, or the config's ec_mode DISABLED at launch. */
+int b200msdf_batch_upload_regions(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
+                                  int transform_per_glyph, const int32_t *dims, int dims_per_glyph, const int32_t *origins,
+                                  int origins_per_glyph, b200msdf_batch **batch);
 /* Enqueues the whole path (contour windings -> distance field -> error correction) for the batch. */
 int b200msdf_batch_launch(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200msdf_config *config);
 /* Same, restricted to some stages (for per-kernel timing): bit 0 windings/prepare, bit 1 distance field, bit 2 error correction.

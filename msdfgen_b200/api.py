@@ -202,14 +202,15 @@ class Context:
         return sdf
 
     # ---- HBM-resident batches --------------------------------------------------------------------------------------
-    def upload(self, mode, shapes: FlatShapes, transformations, dims, out_ydown=None):
-        return Batch(self, mode, shapes, transformations, dims, out_ydown)
+    def upload(self, mode, shapes: FlatShapes, transformations, dims, out_ydown=None, origins=None):
+        """origins: (x0, y0) pixel origin(s) of the output block(s) inside their full image (region batches, SDF/PSDF or EC off)."""
+        return Batch(self, mode, shapes, transformations, dims, out_ydown, origins)
 
 
 class Batch:
     """b200msdf_batch: shapes + geometry resident in HBM, with device output buffers."""
 
-    def __init__(self, ctx: Context, mode, shapes: FlatShapes, transformations, dims, out_ydown=None):
+    def __init__(self, ctx: Context, mode, shapes: FlatShapes, transformations, dims, out_ydown=None, origins=None):
         self.ctx, self.mode, self.n = ctx, mode, shapes.n_glyphs
         xf, per = _transforms(transformations)
         d = np.ascontiguousarray(dims, dtype=np.int32).reshape(-1, 2)
@@ -217,6 +218,11 @@ class Batch:
         yd = np.ascontiguousarray(out_ydown, dtype=np.uint8) if out_ydown is not None else None
         s = _shapes_struct(shapes)
         self.h = C.c_void_p()
+        if origins is not None:
+            o = np.ascontiguousarray(origins, dtype=np.int32).reshape(-1, 2)
+            _lib.check(ctx.lib.b200msdf_batch_upload_regions(ctx.h, mode, C.byref(s), xf, per, d.ctypes.data_as(C.POINTER(C.c_int32)), int(len(d) > 1),
+                                                             o.ctypes.data_as(C.POINTER(C.c_int32)), int(len(o) > 1), C.byref(self.h)))
+            return
         _lib.check(ctx.lib.b200msdf_batch_upload(ctx.h, mode, C.byref(s), xf, per, d.ctypes.data_as(C.POINTER(C.c_int32)), int(len(d) > 1),
                                                  yd.ctypes.data_as(C.POINTER(C.c_uint8)) if yd is not None else None, C.byref(self.h)))
 

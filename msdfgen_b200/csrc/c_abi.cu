@@ -87,6 +87,7 @@ struct b200msdf_batch {
     int maxContours = 0;
     bool hasColors = false;
     bool launched = false;
+    bool regions = false;
     bool ecRan = false;
     DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, field, out, stencil, candidates, candCount;
     std::vector<GlyphDesc> hGlyphs;
@@ -143,7 +144,7 @@ int check_shapes(const b200msdf_shapes *s) {
 
 // Builds per-glyph descriptors + tiles and uploads everything. flips[g] = output orientation != shape orientation.
 int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_shapes *s, const b200msdf_transform *xf, int xfPerGlyph,
-                 const int32_t *dims, int dimsPerGlyph, const uint8_t *outYDown) {
+                 const int32_t *dims, int dimsPerGlyph, const uint8_t *outYDown, const int32_t *origins = nullptr, int originsPerGlyph = 0) {
     if (mode < 1 || mode > 4)
         return fail(B200MSDF_ERR_ARG, "mode %d out of range", mode);
     int rc = check_shapes(s);
@@ -157,6 +158,7 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     b->nSegments = s->n_segments;
     b->hasColors = s->colors != nullptr;
     b->launched = false;
+    b->regions = origins != nullptr;
     b->hGlyphs.resize((size_t) s->n_glyphs);
     b->hTiles.clear();
     b->hBig.clear();
@@ -184,6 +186,10 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
         d.shapeYDown = s->y_downward ? (s->y_downward[g] != 0) : 0;
         int oyd = outYDown ? (outYDown[g] != 0) : 0;
         d.flip = oyd != d.shapeYDown;
+        d.x0 = origins ? origins[originsPerGlyph ? 2*g : 0] : 0;
+        d.y0 = origins ? origins[originsPerGlyph ? 2*g+1 : 1] : 0;
+        if (origins)
+            d.flip = 0;     // regions are generated in the shape's orientation
         d.outOffset = outFloats;
         d.texelOffset = texels;
         size_t px = (size_t) d.w*(size_t) d.h;
@@ -398,6 +404,8 @@ int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
     KernelParams P;
     fill_params(ctx, b, cfg, P);
     bool ec = b->N >= 3 && cfg->ec_mode != B200MSDF_EC_DISABLED;
+    if (ec && b->regions)
+        return fail(B200MSDF_ERR_ARG, "error correction is not available for region batches (needs neighbouring tiles): disable it or generate whole images");
     P.field = ec ? b->field.as<float>() : b->out.as<float>();
     P.out = b->out.as<float>();
     P.stencil = ec ? b->stencil.as<uint8_t>() : nullptr;
@@ -676,6 +684,26 @@ int b200msdf_batch_upload(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *sh
     if (!b)
         return fail(B200MSDF_ERR_ALLOC, "out of host memory");
     rc = upload_batch(ctx, b, mode, shapes, xf, xfPerGlyph, dims, dimsPerGlyph, outYDown);
+    if (rc) {
+        b->release();
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return 0;
+}
+
+int b200msdf_batch_upload_regions(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
+                                  const int32_t *dims, int dimsPerGlyph, const int32_t *origins, int originsPerGlyph, b200msdf_batch **out) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!out || !origins)
+        return fail(B200MSDF_ERR_ARG, "null batch pointer / origins");
+    *out = nullptr;
+    b200msdf_batch *b = new (std::nothrow) b200msdf_batch;
+    if (!b)
+        return fail(B200MSDF_ERR_ALLOC, "out of host memory");
+    rc = upload_batch(ctx, b, mode, shapes, xf, xfPerGlyph, dims, dimsPerGlyph, nullptr, origins, originsPerGlyph);
     if (rc) {
         b->release();
         delete b;

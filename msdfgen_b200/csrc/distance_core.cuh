@@ -104,6 +104,7 @@ struct GlyphDesc {
     int flip;                       // output orientation != shape orientation (rows reversed in memory)
     int shapeYDown;                 // Shape::inverseYAxis
     int nonEmptyContours;
+    int x0, y0;                     // pixel origin of the block inside the full image (regions; 0 otherwise)
     int recBase;                    // >= 0: prepared records live in the global big-shape buffer at this index; -1: staged in smem
 };
 

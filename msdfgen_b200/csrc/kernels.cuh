@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
                 int yOut = int(i/unsigned(w));
                 int y = s_g.flip ? s_g.h-1-yOut : yOut;
                 // Projection::unproject(Point2(x+.5, y+.5))
-                d2 p = mk((x+.5)/s_g.sx-s_g.tx, (y+.5)/s_g.sy-s_g.ty);
+                d2 p = mk((s_g.x0+x+.5)/s_g.sx-s_g.tx, (s_g.y0+y+.5)/s_g.sy-s_g.ty);
                 double dist[NOUT];
                 shape_distance<MODE, OVERLAP>(recs, nRec, p, store, dist);
                 #pragma unroll

@@ -234,3 +234,55 @@ def test_full_atlas_against_compiled_reference(ctx):
         want, _ = ref.generate_batch(mode_name, sub.gbegin, sub.cbegin, sub.points, sub.orders, sub.colors, xf, w, w, glyph_parallel=True)
         bits = assert_parity(got, want, f"full {mode_name} {w}x{w}")
         print(f"[parity] {mode_name} {w}x{w} x{count}: {bits} of {got.size} floats differ in bit pattern, max |delta| {compare(got, want)[1]:.3g}")
+
+
+def test_config4_big_shape_tiles_and_oracle_samples(ctx):
+    """BASELINE configs[3] (one 10k-segment shape, sdf) at reduced resolution: row bands generated as regions are bit-identical
+    to the untiled image, and random texels match ShapeDistanceFinder::oneShotDistance of the oracle (the full generator is
+    too slow on the CPU at this size — SURVEY.md App. B.9)."""
+    from oracle import bindings
+    from msdfgen_b200 import tiled
+    shape = prep.prepare(synth_big_shape(100, 100))
+    assert shape.n_segments == 10000
+    size = 192
+    xf = glyph_transform(size, px_range=8.0)
+    full = np.empty((size, size, 1), np.float32)
+    ctx.generate(api.SDF, full, shape, xf)
+    rows = []
+    for r in range(3):
+        b, (r0, r1) = tiled.generate_band(ctx, api.SDF, shape, xf, size, size, r, 3)
+        assert b.shape[0] == r1 - r0
+        rows.append(b)
+    assert np.array_equal(np.concatenate(rows).view(np.uint32), full.view(np.uint32))
+    oracle = bindings.Oracle("reference" if bindings.ref_available() else "port")
+    rng = np.random.default_rng(4)
+    xs, ys = rng.integers(0, size, 400), rng.integers(0, size, 400)
+    t = xf
+    pts = np.stack([(xs + .5) / t[0] - t[2], (ys + .5) / t[1] - t[3]], axis=1)
+    cb, p, od, cl, _ = shape.glyph(0)
+    d = oracle.distance("sdf", True, cb, p, od, cl, pts)[:, 0]
+    want = (np.float64(1.0) / (t[5] - t[4]) * (d + (-t[4]))).astype(np.float32)
+    got = full[ys, xs, 0]
+    assert_parity(got, want, "config-4 samples")
+    # psdf too (perpendicular selector, many contours -> global contour store)
+    fullp = np.empty((64, 64, 1), np.float32)
+    xfp = glyph_transform(64, px_range=8.0)
+    ctx.generate(api.PSDF, fullp, shape, xfp)
+    xs, ys = rng.integers(0, 64, 200), rng.integers(0, 64, 200)
+    pts = np.stack([(xs + .5) / xfp[0] - xfp[2], (ys + .5) / xfp[1] - xfp[3]], axis=1)
+    d = oracle.distance("psdf", True, cb, p, od, cl, pts)[:, 0]
+    want = (np.float64(1.0) / (xfp[5] - xfp[4]) * (d + (-xfp[4]))).astype(np.float32)
+    assert_parity(fullp[ys, xs, 0], want, "config-4 psdf samples")
+
+
+def test_regions_reject_error_correction(ctx):
+    g = prep.prepare(synth_glyph(3))
+    b = ctx.upload(api.MSDF, g, glyph_transform(16), [16, 8], origins=[0, 4])
+    with pytest.raises(Exception):
+        b.launch(api.MSDFGeneratorConfig())
+    b.launch(api.MSDFGeneratorConfig(errorCorrection=api.ErrorCorrectionConfig(mode=api.EC_DISABLED)))
+    part = b.download()[: 8 * 16 * 3].reshape(8, 16, 3)
+    full = np.empty((16, 16, 3), np.float32)
+    ctx.generate(api.MSDF, full, g, glyph_transform(16), api.MSDFGeneratorConfig(errorCorrection=api.ErrorCorrectionConfig(mode=api.EC_DISABLED)))
+    assert np.array_equal(part.view(np.uint32), full[4:12].view(np.uint32))
+    b.free()

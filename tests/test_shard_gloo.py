@@ -66,3 +66,46 @@ def test_partition_edge_cases():
     assert b[0] == 0 and b[-1] == 10 and (np.diff(b) >= 0).all()
     b = shard.partition([100, 1, 1, 1], 4)
     assert b[0] == 0 and b[-1] == 4 and (np.diff(b) >= 0).all()
+
+
+def test_band_partition():
+    from msdfgen_b200 import tiled
+    for h in (0, 1, 7, 4096):
+        for world in (1, 2, 3, 8):
+            bands = [tiled.band(h, r, world) for r in range(world)]
+            assert bands[0][0] == 0 and bands[-1][1] == h
+            assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
+            assert max(b[1] - b[0] for b in bands) - min(b[1] - b[0] for b in bands) <= 1
+
+
+def _bcast_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from msdfgen_b200 import tiled
+    from msdfgen_b200.synth import synth_big_shape
+    shape = synth_big_shape(5, 7) if rank == 0 else None
+    got = tiled.broadcast_shape(shape, 0, None)
+    want = synth_big_shape(5, 7)
+    ok = all(np.array_equal(getattr(got, n), getattr(want, n)) for n in ("gbegin", "cbegin", "points", "orders", "colors", "ydown"))
+    oks = [None] * world
+    dist.all_gather_object(oks, ok)
+    if rank == 0:
+        q.put(oks)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_segment_pool_broadcast_two_ranks():
+    """The one collective of the tiled single-shape path: rank 0's flat shape arrays arrive intact on every rank."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    oks = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert oks == [True, True]
