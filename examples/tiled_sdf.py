@@ -36,7 +36,7 @@ def main():
         shape = tiled.broadcast_shape(shape, 0, torch.device("cuda", local))
     xf = glyph_transform(args.size, px_range=8.0)
     ctx = api.Context(local)
-    tiled.generate_band(ctx, api.SDF, shape, xf, args.size, min(args.size, 64 * world), rank, world)     # warm-up
+    tiled.generate_band(ctx, api.SDF, shape, xf, args.size, args.size, rank, world)     # warm-up: module load, buffer growth
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
