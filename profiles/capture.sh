@@ -1,0 +1,12 @@
+#!/bin/bash
+# Run on the GPU box (gpurun): ncu launch list of bench.py + one full capture per hot kernel. Outputs under gpurun_out/.
+# Usage: /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash profiles/capture.sh r1'
+tag=${1:-r1}
+mkdir -p gpurun_out
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_under_ncu_${tag}.log 2>&1
+for k in k1_distance_field k2_classify k3_exact_distance; do
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -o gpurun_out/${k}_${tag} \
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_${k}_${tag}.log 2>&1
+done
+ls -la gpurun_out/*_${tag}*
