@@ -333,7 +333,8 @@ __device__ __forceinline__ Roots solve_quadratic(double a, double b, double c) {
     return r;
 }
 
-__device__ __forceinline__ Roots solve_cubic_normed(double a, double b, double c) {
+// (cold: only reached from the fast path when its fp32 stage cannot represent the coefficients — kept out of line)
+__device__ __noinline__ Roots solve_cubic_normed(double a, double b, double c) {
     Roots x; x.t0 = x.t1 = x.t2 = 0;
     double a2 = a*a;
     double q = 1/9.*(a2-3*b);
@@ -379,7 +380,7 @@ __device__ __forceinline__ Roots solve_cubic_normed(double a, double b, double c
 #define B200_EXACT_ROOTS 0
 #endif
 
-__device__ __forceinline__ double cubic_polish(double t, double A, double B, double C) {
+__device__ __noinline__ double cubic_polish(double t, double A, double B, double C) {
     #pragma unroll
     for (int i = 0; i < 3; ++i) {
         double f = fma(fma(t+A, t, B), t, C);
@@ -642,14 +643,16 @@ __device__ __forceinline__ void chan_merge(Chan &c, const Chan &o) {
         if (o.pos < c.pos) c.pos = o.pos;
     }
 }
-// computeDistance
-__device__ __forceinline__ double chan_distance(const Chan &c, const SegRec *recs, d2 p) {
-    double m = c.d < 0 ? c.neg : c.pos;
-    if (c.near >= 0) {
-        double dd = c.d;
-        int side = c.near&3;
+// computeDistance (edge-selectors.cpp:108-117), once per contour and channel: out of line (by value, so that the selector
+// state stays in registers) to keep the kernels' instruction footprint small
+__device__ __noinline__ double chan_distance_values(double cd, double neg, double pos, int near, const SegRec *recs, double px, double py) {
+    d2 p = mk(px, py);
+    double m = cd < 0 ? neg : pos;
+    if (near >= 0) {
+        double dd = cd;
+        int side = near&3;
         if (side) {
-            const SegRec &s = recs[c.near>>2];
+            const SegRec &s = recs[near>>2];
             if (side == 1) {
                 d2 aq = p-s.p0;
                 double ts = dot(aq, s.aDirNZ);
@@ -672,6 +675,9 @@ __device__ __forceinline__ double chan_distance(const Chan &c, const SegRec *rec
             m = dd;
     }
     return m;
+}
+__device__ __forceinline__ double chan_distance(const Chan &c, const SegRec *recs, d2 p) {
+    return chan_distance_values(c.d, c.neg, c.pos, c.near, recs, p.x, p.y);
 }
 
 template <int MODE> struct Sel { Chan ch[ModeTraits<MODE>::NCH]; };

@@ -569,9 +569,15 @@ __device__ __forceinline__ void patch_texel(const KernelParams &P, const GlyphDe
 template <int N, bool OVERLAP, bool BIG>
 __global__ void __launch_bounds__(K3_THREADS) k3_exact_distance(KernelParams P) {
     __shared__ SegRec s_recs[BIG ? 1 : SMEM_RECORDS];
+    __shared__ __align__(16) double s_points[BIG ? 2 : SMEM_RECORDS*8];
+    __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ GlyphDesc s_g;
     double localStore[B200_LOCAL_CONTOURS*StoreLayout<2>::PER_CONTOUR];
     const int lane = threadIdx.x;
+    unsigned phase = 0;
+    if (!BIG && lane == 0)
+        mbar_init(&s_mbar);
+    __syncwarp();
     int stagedGlyph = -1;
     for (;;) {
         int tile = 0;
@@ -590,7 +596,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_exact_distance(KernelParams P) 
                 s_g = P.glyphs[td.glyph];
             __syncwarp();
             if (!BIG)
-                stage_glyph(P, s_g, s_recs);
+                stage_glyph(P, s_g, s_recs, s_points, &s_mbar, phase);
             stagedGlyph = (int) td.glyph;
             __syncwarp();
         }

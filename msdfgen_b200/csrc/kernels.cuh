@@ -76,11 +76,46 @@ struct TileCursor {
     int glyph;
 };
 
-// Small glyphs (<= SMEM_RECORDS segments): every thread of the CTA prepares records into shared memory.
-__device__ __forceinline__ void stage_glyph(const KernelParams &P, const GlyphDesc &g, SegRec *smemRecs) {
+// ---- TMA (bulk async copy) staging of a glyph's raw control points ---------------------------------------------------------
+// One elected thread issues cp.async.bulk (global -> shared, completion counted in bytes on an mbarrier); the CTA waits on
+// the barrier's phase and then prepares the records from shared memory.  SASS: UBLKCP + SYNCS.
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void tma_load_1d(void *dstSmem, const void *srcGlobal, unsigned bytes, unsigned long long *mbar) {
+    unsigned bar = smem_addr(mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *mbar, unsigned phase) {
+    unsigned bar = smem_addr(mbar);
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+}
+
+// Small glyphs (<= SMEM_RECORDS segments): the raw control points arrive in shared memory by one TMA bulk copy, then every
+// thread of the CTA prepares records from them.  `phase` is the CTA-uniform parity of the mbarrier (flipped per use).
+__device__ __forceinline__ void stage_glyph(const KernelParams &P, const GlyphDesc &g, SegRec *smemRecs, double *smemPoints,
+                                            unsigned long long *mbar, unsigned &phase) {
     unsigned n = g.s1-g.s0;
+    if (n == 0)
+        return;
+    if (threadIdx.x == 0)
+        tma_load_1d(smemPoints, P.raw.points+8*size_t(g.s0), n*64u, mbar);
+    mbar_wait(mbar, phase);
+    phase ^= 1u;
+    RawShapes rs = P.raw;
+    rs.points = smemPoints-8*size_t(g.s0);       // prepare_record indexes segments by their global index
     for (unsigned j = threadIdx.x; j < n; j += blockDim.x)
-        prepare_record(P.raw, g, j, smemRecs[j]);
+        prepare_record(rs, g, j, smemRecs[j]);
 }
 
 // Coalesced write-back of nFloats staged floats to dst (16-byte aligned when aligned == true).
@@ -105,9 +140,14 @@ template <int MODE, bool OVERLAP, bool BIG>
 __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams P) {
     const int NOUT = ModeTraits<MODE>::NOUT;
     __shared__ SegRec s_recs[BIG ? 1 : SMEM_RECORDS];
+    __shared__ __align__(16) double s_points[BIG ? 2 : SMEM_RECORDS*8];
+    __shared__ __align__(8) unsigned long long s_mbar;
     __shared__ __align__(16) float s_out[CTA_THREADS*NOUT];
     __shared__ GlyphDesc s_g;
     __shared__ int s_tile;
+    unsigned phase = 0;
+    if (!BIG && threadIdx.x == 0)
+        mbar_init(&s_mbar);
 
     double localStore[OVERLAP ? B200_LOCAL_CONTOURS*StoreLayout<MODE>::PER_CONTOUR : 1];
     int stagedGlyph = -1;
@@ -125,7 +165,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
                 s_g = P.glyphs[td.glyph];
             __syncthreads();
             if (!BIG)
-                stage_glyph(P, s_g, s_recs);
+                stage_glyph(P, s_g, s_recs, s_points, &s_mbar, phase);
             stagedGlyph = (int) td.glyph;
             __syncthreads();
         }
