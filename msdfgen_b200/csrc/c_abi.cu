@@ -8,6 +8,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <unordered_map>
 #include <new>
 #include <string>
 #include <vector>
@@ -88,14 +90,16 @@ struct b200msdf_batch {
     bool hasColors = false;
     bool launched = false;
     bool regions = false;
+    float *outOverride = nullptr;   // final texels go here instead of `out` (device-accessible pinned host memory of the caller)
     bool ecRan = false;
     DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, field, out, stencil, candidates, candCount;
+    DevBuf counters, scratch;     // per batch, so that batches launched on different streams never share scheduling state
     std::vector<GlyphDesc> hGlyphs;
     std::vector<TileDesc> hTiles;
     std::vector<int> hBig;
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
-        bigGlyphs.release(); bigRecs.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release();
+        bigGlyphs.release(); bigRecs.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release();
     }
 };
 
@@ -103,10 +107,12 @@ struct b200msdf_ctx {
     int device = 0;
     int numSMs = 0;
     cudaStream_t own = nullptr, stream = nullptr;
-    DevBuf counters, scratch;
+    cudaStream_t aux[2] = { nullptr, nullptr };     // double-buffered chunks of large host batches (copy/compute overlap)
     PinBuf pinOut, pinIn;
     uint64_t launches = 0;
-    b200msdf_batch pool;    // reused by the host-buffer entry points
+    b200msdf_batch pool;        // reused by the host-buffer entry points
+    b200msdf_batch chunk[2];    // reused by the chunked host path
+    b200msdf_batch *cur = nullptr;
 };
 
 namespace {
@@ -228,6 +234,7 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     if ((rc = b->glyphs.reserve(sizeof(GlyphDesc)*(b->hGlyphs.size()+1)))) return rc;
     if ((rc = b->tiles.reserve(sizeof(TileDesc)*(b->hTiles.size()+1)))) return rc;
     if ((rc = b->out.reserve(outFloats*4+64))) return rc;
+    if ((rc = b->counters.reserve(64))) return rc;
     if (b->N >= 3) {
         if ((rc = b->field.reserve(outFloats*4+64))) return rc;
         if ((rc = b->stencil.reserve(texels+64))) return rc;
@@ -258,10 +265,18 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
 
 template <typename K>
 int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, size_t dynSmem, int threads, int *grid) {
+    // resident CTAs per SM of this kernel: queried once per kernel and cached (the query costs microseconds per launch)
+    static thread_local std::unordered_map<const void *, int> cache;
     int perSM = 0;
-    if (dynSmem)
-        CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dynSmem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, dynSmem));
+    auto it = cache.find((const void *) kernel);
+    if (it != cache.end())
+        perSM = it->second;
+    else {
+        if (dynSmem)
+            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dynSmem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, dynSmem));
+        cache[(const void *) kernel] = perSM;
+    }
     if (perSM < 1) perSM = 1;
     long long g = (long long) perSM*ctx->numSMs;
     *grid = (int) (g < nTiles ? g : nTiles);
@@ -277,8 +292,8 @@ int launch_tiles(b200msdf_ctx *ctx, K kernel, KernelParams &P, int perThreadDoub
     if ((rc = grid_for(ctx, kernel, P.tileEnd-P.tileBegin, dynSmem, threads, &grid))) return rc;
     P.scratchStride = (size_t) grid*threads;
     if (perThreadDoubles > 0) {
-        if ((rc = ctx->scratch.reserve(P.scratchStride*(size_t) perThreadDoubles*sizeof(double)))) return rc;
-        P.scratch = ctx->scratch.as<double>();
+        if ((rc = ctx->cur->scratch.reserve(P.scratchStride*(size_t) perThreadDoubles*sizeof(double)))) return rc;
+        P.scratch = ctx->cur->scratch.as<double>();
     } else
         P.scratch = nullptr;
     kernel<<<grid, threads, dynSmem, ctx->stream>>>(P);
@@ -363,7 +378,8 @@ void fill_params(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
     P.counterIndex = 0;
     P.nContours = b->nContours;
     P.bigRecs = b->bigRecs.as<SegRec>();
-    P.counters = ctx->counters.as<int>();
+    P.counters = b->counters.as<int>();
+    ctx->cur = b;
     P.ecMode = cfg->ec_mode;
     P.ecDcm = cfg->ec_distance_check_mode;
     P.minDeviationRatio = cfg->min_deviation_ratio;
@@ -406,8 +422,9 @@ int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
     bool ec = b->N >= 3 && cfg->ec_mode != B200MSDF_EC_DISABLED;
     if (ec && b->regions)
         return fail(B200MSDF_ERR_ARG, "error correction is not available for region batches (needs neighbouring tiles): disable it or generate whole images");
-    P.field = ec ? b->field.as<float>() : b->out.as<float>();
-    P.out = b->out.as<float>();
+    float *finalOut = b->outOverride ? b->outOverride : b->out.as<float>();
+    P.field = ec ? b->field.as<float>() : finalOut;
+    P.out = finalOut;
     P.stencil = ec ? b->stencil.as<uint8_t>() : nullptr;
     if (stages&1u)
         if ((rc = launch_prologue(ctx, b, P))) return rc;
@@ -524,8 +541,10 @@ int b200msdf_create(int device, b200msdf_ctx **out) {
     e = cudaStreamCreateWithFlags(&ctx->own, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(B200MSDF_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     ctx->stream = ctx->own;
-    int rc = ctx->counters.reserve(64);
-    if (rc) { cudaStreamDestroy(ctx->own); delete ctx; return rc; }
+    for (int i = 0; i < 2; ++i) {
+        e = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; return fail(B200MSDF_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    }
     *out = ctx;
     return 0;
 }
@@ -534,9 +553,11 @@ void b200msdf_destroy(b200msdf_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); }
+        ctx->chunk[i].release();
+    }
     ctx->pool.release();
-    ctx->counters.release();
-    ctx->scratch.release();
     ctx->pinOut.release();
     ctx->pinIn.release();
     if (ctx->own) cudaStreamDestroy(ctx->own);
@@ -573,6 +594,50 @@ int b200msdf_host_alloc(void **ptr, size_t bytes) {
 
 void b200msdf_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
 
+namespace {
+
+// A glyph range [g0, g1) of a batch as an independent batch (index arrays rebased on the host: O(contours)).
+struct SubShapes {
+    b200msdf_shapes view;
+    std::vector<uint32_t> gcb, csb;
+    SubShapes(const b200msdf_shapes *s, int g0, int g1) {
+        uint32_t c0 = s->glyph_contour_begin[g0], c1 = s->glyph_contour_begin[g1];
+        uint32_t s0 = s->contour_segment_begin[c0], s1 = s->contour_segment_begin[c1];
+        gcb.resize((size_t) (g1-g0)+1);
+        for (int g = g0; g <= g1; ++g)
+            gcb[(size_t) (g-g0)] = s->glyph_contour_begin[g]-c0;
+        csb.resize((size_t) (c1-c0)+1);
+        for (uint32_t k = c0; k <= c1; ++k)
+            csb[k-c0] = s->contour_segment_begin[k]-s0;
+        view.n_glyphs = g1-g0;
+        view.n_contours = (int32_t) (c1-c0);
+        view.n_segments = (int32_t) (s1-s0);
+        view.glyph_contour_begin = gcb.data();
+        view.contour_segment_begin = csb.data();
+        view.points = s->points ? s->points+8*(size_t) s0 : nullptr;
+        view.orders = s->orders ? s->orders+s0 : nullptr;
+        view.colors = s->colors ? s->colors+s0 : nullptr;
+        view.y_downward = s->y_downward ? s->y_downward+g0 : nullptr;
+    }
+};
+
+// Are the caller's sections one packed block in device layout (every glyph [h][w][N] contiguous, blocks back to back at
+// 16-byte multiples)?  Then results can be DMA'd straight into them, chunk by chunk.
+bool packed_outputs(const b200msdf_bitmap *bm, int n, int N) {
+    size_t off = 0;
+    for (int g = 0; g < n; ++g) {
+        size_t fl = (size_t) bm[g].width*bm[g].height*N;
+        if (fl == 0)
+            continue;
+        if (bm[g].row_stride != bm[g].width*N || bm[g].pixels != bm[0].pixels+off || (fl&3))
+            return false;
+        off += fl;
+    }
+    return n > 0 && bm[0].pixels != nullptr;
+}
+
+}  // namespace
+
 int b200msdf_generate_batch(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
                             const b200msdf_bitmap *outputs, const b200msdf_config *config) {
     int rc = bind(ctx);
@@ -582,13 +647,64 @@ int b200msdf_generate_batch(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *
     if ((rc = check_bitmaps(outputs, shapes->n_glyphs))) return rc;
     if (shapes->n_glyphs == 0)
         return 0;
+    if (mode < 1 || mode > 4)
+        return fail(B200MSDF_ERR_ARG, "mode %d out of range", mode);
     std::vector<int32_t> dims;
     std::vector<uint8_t> yd;
     dims_from_bitmaps(outputs, shapes->n_glyphs, dims, yd);
+    const int n = shapes->n_glyphs;
+    // Large atlases into one packed block: split into chunks on two streams so that the D2H of one chunk overlaps the
+    // kernels of the next (the output is 5x the input, so the transfer is almost entirely D2H).
+    // (measured on B200 / PCIe Gen5: the per-chunk launch and tail overhead cancels the overlap for the headline workload, so
+    // chunking is opt-in; the zero-copy output path below is what removes the D2H from the critical path)
+    int chunks = 1;
+    if (const char *env = getenv("B200MSDF_CHUNKS"))
+        chunks = atoi(env) > 0 ? atoi(env) : 1;
+    if (chunks > 1 && ctx->stream == ctx->own && packed_outputs(outputs, n, channels_of(mode))) {
+        cudaStream_t saved = ctx->stream;
+        rc = 0;
+        for (int c = 0; c < chunks && !rc; ++c) {
+            int g0 = (int) ((long long) n*c/chunks), g1 = (int) ((long long) n*(c+1)/chunks);
+            if (g1 <= g0)
+                continue;
+            b200msdf_batch *b = &ctx->chunk[c&1];
+            ctx->stream = ctx->aux[c&1];
+            SubShapes sub(shapes, g0, g1);
+            rc = upload_batch(ctx, b, mode, &sub.view, xf+(xfPerGlyph ? g0 : 0), xfPerGlyph, dims.data()+2*(size_t) g0, 1, yd.data()+g0);
+            if (!rc) rc = launch_batch(ctx, b, config);
+            if (!rc && b->outFloats) {
+                const GlyphDesc &last = b->hGlyphs.back();
+                size_t floats = last.outOffset+(size_t) last.w*last.h*b->N;
+                cudaError_t e = cudaMemcpyAsync(outputs[g0].pixels, b->out.p, floats*4, cudaMemcpyDeviceToHost, ctx->stream);
+                if (e != cudaSuccess)
+                    rc = fail(B200MSDF_ERR_CUDA, "cudaMemcpyAsync D2H: %s", cudaGetErrorString(e));
+            }
+        }
+        ctx->stream = saved;
+        cudaError_t e0 = cudaStreamSynchronize(ctx->aux[0]), e1 = cudaStreamSynchronize(ctx->aux[1]);
+        if (!rc && (e0 != cudaSuccess || e1 != cudaSuccess))
+            rc = fail(B200MSDF_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1));
+        return rc;
+    }
     b200msdf_batch *b = &ctx->pool;
     if ((rc = upload_batch(ctx, b, mode, shapes, xf, xfPerGlyph, dims.data(), 1, yd.data()))) return rc;
-    if ((rc = launch_batch(ctx, b, config))) return rc;
-    if ((rc = download_to_bitmaps(ctx, b, b->out.as<float>(), outputs))) return rc;
+    // Zero-copy output: when the caller's sections form one packed block of pinned, device-accessible host memory (e.g. from
+    // b200msdf_host_alloc), the kernels store the final texels straight into it over PCIe (coalesced float4 rows, posted
+    // writes) while they are still computing, instead of a separate D2H copy after the last kernel.
+    float *direct = nullptr;
+    if (packed_outputs(outputs, n, channels_of(mode)) && !getenv("B200MSDF_NO_ZEROCOPY")) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, outputs[0].pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            direct = static_cast<float *>(attr.devicePointer);
+        else
+            cudaGetLastError();
+    }
+    b->outOverride = direct;
+    rc = launch_batch(ctx, b, config);
+    b->outOverride = nullptr;
+    if (rc) return rc;
+    if (!direct)
+        if ((rc = download_to_bitmaps(ctx, b, b->out.as<float>(), outputs))) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -286,3 +286,18 @@ def test_regions_reject_error_correction(ctx):
     ctx.generate(api.MSDF, full, g, glyph_transform(16), api.MSDFGeneratorConfig(errorCorrection=api.ErrorCorrectionConfig(mode=api.EC_DISABLED)))
     assert np.array_equal(part.view(np.uint32), full[4:12].view(np.uint32))
     b.free()
+
+
+def test_zero_copy_pinned_output_equals_copied_output(ctx):
+    """Packed pinned host output (b200msdf_host_alloc) takes the zero-copy path (kernels store straight into host memory);
+    pageable output takes the staged D2H path. Same texels either way, for every mode and with error correction on."""
+    atlas = prep.prepare(synth_atlas(300, seed=777))
+    xf = glyph_transform(32)
+    for mode in (api.SDF, api.MSDF, api.MTSDF):
+        n = api.CHANNELS[mode]
+        pageable = np.full((300, 32, 32, n), np.nan, np.float32)
+        pinned = ctx.pinned((300, 32, 32, n), np.float32)
+        pinned[...] = np.nan
+        ctx.generate_batch(mode, pageable, atlas, xf)
+        ctx.generate_batch(mode, pinned, atlas, xf)
+        assert np.array_equal(pageable.view(np.uint32), np.asarray(pinned).view(np.uint32))
