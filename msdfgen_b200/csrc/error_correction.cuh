@@ -181,10 +181,6 @@ __device__ __forceinline__ float interp_median_quad(const float *a, const float 
 // hasLinearArtifactInner (:279-289)
 template <int N, int SINK, bool OVERLAP>
 __device__ __noinline__ void linear_artifact_inner(const EcCtx<N> &e, TexelState &k, float am, float bm, const float *a, const float *b, float dA, float dB) {
-    // t = dA/(dA-dB) lies strictly inside (0,1) only if dA and dB have strictly opposite signs; in every other case the
-    // reference's range test (t > .01 && t < .99) fails as well, so the fp64 division is skipped without changing a result.
-    if (!((dA > 0 && dB < 0) || (dA < 0 && dB > 0)))
-        return;
     double t = double(dA)/(dA-dB);
     if (t > ARTIFACT_T_EPSILON && t < 1-ARTIFACT_T_EPSILON) {
         float xm = interp_median_lin(a, b, t);
@@ -194,19 +190,19 @@ __device__ __noinline__ void linear_artifact_inner(const EcCtx<N> &e, TexelState
     }
 }
 
+// Local extremes of the three channels along one diagonal (tEx of hasDiagonalArtifact :364-369) and the interpolated medians
+// there, computed on first use and shared by the three channel-pair tests of that diagonal.
+struct DiagonalExtremes {
+    double tEx[3];
+    float median[3];
+    int have;       // bit k: tEx[k] (and, if inside (0,1), median[k]) are valid
+};
+
 // hasDiagonalArtifactInner (:293-329)
 template <int N, int SINK, bool OVERLAP>
 __device__ __noinline__ void diagonal_artifact_inner(const EcCtx<N> &e, TexelState &k, float am, float dm, const float *a, const float *l, const float *q,
-                                                        float dA, float dBC, float dD, int ex0, int ex1) {
-    // Two channels are equal where f(t) = qa t^2 + qb t + qc vanishes.  f has a zero strictly inside (0,1) only if it
-    // changes sign between t = 0 and t = 1 or has its vertex inside (0,1); otherwise the reference's roots all fall outside
-    // its (.01, .99) window, so the square root and divisions of solveQuadratic are skipped without changing a result.
+                                                        float dA, float dBC, float dD, int ex0, int ex1, DiagonalExtremes &x) {
     const double qa = dD-dBC+dA, qb = dBC-dA-dA, qc = dA;
-    const double f1 = qa+qb+qc;
-    const bool signChange = (qc > 0 && f1 < 0) || (qc < 0 && f1 > 0);
-    const bool vertexInside = (qa > 0 && qb < 0 && -qb < 2*qa) || (qa < 0 && qb > 0 && qb < -2*qa);
-    if (!(signChange || vertexInside))
-        return;
     Roots r = solve_quadratic(qa, qb, qc);
     for (int i = 0; i < r.n; ++i) {
         double ti = i == 0 ? r.t0 : r.t1;
@@ -214,17 +210,22 @@ __device__ __noinline__ void diagonal_artifact_inner(const EcCtx<N> &e, TexelSta
             float xm = interp_median_quad(a, l, q, ti);
             int fb = k.useBase ? range_test(k.protBase, k.span, 0, 1, ti, am, dm, xm) : 0;
             int fs = k.useShape ? range_test(k.protShape, k.span, 0, 1, ti, am, dm, xm) : 0;
-            #pragma unroll
+            #pragma unroll 1
             for (int ex = 0; ex < 2; ++ex) {
                 int ch = ex == 0 ? ex0 : ex1;
-                // local extreme of channel ch along the diagonal: 2*q*t + l == 0
-                float lc = ch == 0 ? l[0] : ch == 1 ? l[1] : l[2];
-                float qc2 = ch == 0 ? q[0] : ch == 1 ? q[1] : q[2];
-                double tEx = -.5*lc/qc2;
+                if (!((x.have>>ch)&1)) {
+                    // local extreme of channel ch along the diagonal: 2*q*t + l == 0
+                    double t = -.5*l[ch]/q[ch];
+                    x.tEx[ch] = t;
+                    if (t > 0 && t < 1)
+                        x.median[ch] = interp_median_quad(a, l, q, t);
+                    x.have |= 1<<ch;
+                }
+                double tEx = x.tEx[ch];
                 if (tEx > 0 && tEx < 1) {
                     double tEnd0 = 0, tEnd1 = 1;
                     float em0 = am, em1 = dm;
-                    float exm = interp_median_quad(a, l, q, tEx);
+                    float exm = x.median[ch];
                     if (tEx > ti) { tEnd1 = tEx; em1 = exm; } else { tEnd0 = tEx; em0 = exm; }
                     if (k.useBase) fb |= range_test(k.protBase, k.span, tEnd0, tEnd1, ti, em0, em1, xm);
                     if (k.useShape) fs |= range_test(k.protShape, k.span, tEnd0, tEnd1, ti, em0, em1, xm);
@@ -267,7 +268,12 @@ __device__ __forceinline__ void find_errors_texel(const EcCtx<N> &e, TexelState 
         for (int pr = 0; pr < 3; ++pr) {
             float a0 = pr == 0 ? a[0] : pr == 1 ? a[1] : a[2], a1 = pr == 0 ? a[1] : pr == 1 ? a[2] : a[0];
             float b0 = pr == 0 ? b[0] : pr == 1 ? b[1] : b[2], b1 = pr == 0 ? b[1] : pr == 1 ? b[2] : b[0];
-            linear_artifact_inner<N, SINK, OVERLAP>(e, k, am, bm, a, b, a1-a0, b1-b0);
+            // t = dA/(dA-dB) lies strictly inside (0,1) only if dA and dB have strictly opposite signs; in every other case
+            // the reference's range test (t > .01 && t < .99) fails as well, so the out-of-line test with its fp64 division
+            // is skipped without changing a result.
+            float dA = a1-a0, dB = b1-b0;
+            if ((dA > 0 && dB < 0) || (dA < 0 && dB > 0))
+                linear_artifact_inner<N, SINK, OVERLAP>(e, k, am, bm, a, b, dA, dB);
         }
     }
     // diagonally adjacent texels: hasDiagonalArtifact (:349-381) with b = horizontal, c = vertical neighbour
@@ -291,6 +297,8 @@ __device__ __forceinline__ void find_errors_texel(const EcCtx<N> &e, TexelState 
         float abc[3] = { a[0]-b[0]-cc[0], a[1]-b[1]-cc[1], a[2]-b[2]-cc[2] };
         float l[3] = { -a[0]-abc[0], -a[1]-abc[1], -a[2]-abc[2] };
         float q[3] = { d[0]+abc[0], d[1]+abc[1], d[2]+abc[2] };
+        DiagonalExtremes extremes;
+        extremes.have = 0;
         #pragma unroll 1
         for (int pr = 0; pr < 3; ++pr) {
             const int i0 = pr, i1 = pr == 2 ? 0 : pr+1;
@@ -298,7 +306,20 @@ __device__ __forceinline__ void find_errors_texel(const EcCtx<N> &e, TexelState 
             float a0 = B200_PICK(a, i0), a1 = B200_PICK(a, i1), b0 = B200_PICK(b, i0), b1 = B200_PICK(b, i1);
             float c0 = B200_PICK(cc, i0), c1 = B200_PICK(cc, i1), d0 = B200_PICK(d, i0), d1 = B200_PICK(d, i1);
             #undef B200_PICK
-            diagonal_artifact_inner<N, SINK, OVERLAP>(e, k, am, dm, a, l, q, a1-a0, b1-b0+c1-c0, d1-d0, i0, i1);
+            // Two channels are equal where f(t) = qa t^2 + qb t + qc vanishes.  f has a zero strictly inside (0,1) only if
+            // it changes sign between t = 0 and t = 1 or has its vertex inside (0,1); otherwise the reference's roots all
+            // fall outside its (.01, .99) window, so the out-of-line test with the square root and divisions of
+            // solveQuadratic is skipped without changing a result.
+            float dA = a1-a0, dBC = b1-b0+c1-c0, dD = d1-d0;
+            const double qa = dD-dBC+dA, qb = dBC-dA-dA, qc = dA;
+            const double f1 = qa+qb+qc;
+            const bool signChange = (qc > 0 && f1 < 0) || (qc < 0 && f1 > 0);
+            // without a sign change both roots must lie inside [0,1): vertex inside, f(0) not on the far side of the
+            // parabola's opening (f(0) == 0 is the frequent "two channels equal at the texel" case: the other root may be
+            // inside), and a non-negative discriminant (the very expression solveQuadratic evaluates)
+            const bool vertexInside = (qa > 0 && qb < 0 && -qb < 2*qa && qc >= 0) || (qa < 0 && qb > 0 && qb < -2*qa && qc <= 0);
+            if (signChange || (vertexInside && qb*qb-4*qa*qc >= 0))
+                diagonal_artifact_inner<N, SINK, OVERLAP>(e, k, am, dm, a, l, q, dA, dBC, dD, i0, i1, extremes);
         }
     }
 }

@@ -52,11 +52,20 @@ def test_no_cpu_fallback_without_device():
 
 
 def test_product_does_not_reference_the_oracle():
-    """The shipped library and package must not import, link or load anything under oracle/."""
+    """The shipped library and package must not import, link or load anything under oracle/ (it is test infrastructure)."""
     pkg = os.path.join(ROOT, "msdfgen_b200")
+    banned = ("libmsdf_oracle", "libmsdfgen_ref", "from oracle", "import oracle", "oracle.bindings", "msdf_oracle.c", "ref_wrapper")
+    checked = 0
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="replace").read()
-                assert "oracle/" not in text.replace("no oracle", "") or "never links" in text or f.endswith(".py") and "oracle" not in text.split('"""')[-1], (dirpath, f)
-                assert "libmsdf_oracle" not in text and "libmsdfgen_ref" not in text and "from oracle" not in text and "import oracle" not in text, (dirpath, f)
+                checked += 1
+                for b in banned:
+                    assert b not in text, (os.path.join(dirpath, f), b)
+    assert checked > 10
+    # and the built libraries do not depend on the oracle's shared objects
+    import subprocess
+    for lib in ("libmsdfgen_b200.so", "libmsdfgen_b200_host.so"):
+        out = subprocess.run(["ldd", os.path.join(pkg, lib)], capture_output=True, text=True).stdout
+        assert "oracle" not in out and "msdfgen_ref" not in out
