@@ -183,8 +183,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
             store.base = localStore;
             store.stride = 1;
         }
+        // Thread -> texel mapping inside a pass of CTA_THREADS consecutive texels.  When the pass is a whole number of rows
+        // (w in {8,16,32,64}) a warp takes an 8x4 block instead of a 32x1 strip: neighbouring lanes then see nearly the same
+        // set of relevant edges, so the culling branches and the segment kernels' branches diverge less.
+        const bool blocked = (w&7) == 0 && w <= 64 && (CTA_THREADS%w) == 0 && ((CTA_THREADS/w)&3) == 0;
         for (unsigned passBase = td.pix0; passBase < tileEnd; passBase += CTA_THREADS) {
-            unsigned i = passBase+threadIdx.x;
+            unsigned slot = threadIdx.x;        // position of this thread's texel inside the pass (row-major)
+            if (blocked && passBase+CTA_THREADS <= tileEnd) {
+                const unsigned warp = threadIdx.x>>5, lane = threadIdx.x&31;
+                const unsigned blocksAcross = unsigned(w)>>3;
+                unsigned bx = warp%blocksAcross, by = warp/blocksAcross;
+                slot = (by*4+(lane>>3))*unsigned(w)+bx*8+(lane&7);
+            }
+            unsigned i = passBase+slot;
             if (i < tileEnd) {
                 int x = int(i%unsigned(w));
                 int yOut = int(i/unsigned(w));
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
                 shape_distance<MODE, OVERLAP>(recs, nRec, p, store, dist);
                 #pragma unroll
                 for (int k = 0; k < NOUT; ++k)
-                    s_out[threadIdx.x*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));    // DistanceMapping::operator()
+                    s_out[slot*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));    // DistanceMapping::operator()
             }
             __syncthreads();
             unsigned nPix = tileEnd-passBase < CTA_THREADS ? tileEnd-passBase : CTA_THREADS;
