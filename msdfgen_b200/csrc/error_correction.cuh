@@ -465,6 +465,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
         const int nRec = needCorners ? int(s_g.s1-s_g.s0) : 0;
         const SegRec *bigRecs = s_g.recBase >= 0 ? P.bigRecs+s_g.recBase : nullptr;
         unsigned tileEnd = td.pix0+TILE_PIXELS < total ? td.pix0+TILE_PIXELS : total;
+        const bool blocked = (w&7) == 0 && w <= 256 && td.pix0%unsigned(w) == 0 && (tileEnd-td.pix0)%(4u*unsigned(w)) == 0;
 
         EcCtx<N> e;
         e.f.base = P.field+s_g.outOffset;
@@ -486,6 +487,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
             if (chunkBase >= tileEnd)
                 break;
             unsigned i = chunkBase+lane;
+            // 8x4 texel blocks instead of 32x1 strips when the tile is a whole number of 4-row groups: lanes of a warp then
+            // share most of their 3x3 neighbourhoods (cache lines) and take more similar branches
+            unsigned blockOrigin = 0;
+            if (blocked) {
+                const unsigned blocksAcross = unsigned(w)>>3;
+                unsigned bx = unsigned(chunk)%blocksAcross, by = unsigned(chunk)/blocksAcross;
+                blockOrigin = td.pix0+by*4u*unsigned(w)+bx*8u;
+                i = blockOrigin+unsigned(lane>>3)*unsigned(w)+unsigned(lane&7);
+            }
             if (i < tileEnd) {
                 int x = int(i%unsigned(w));
                 int yOut = int(i/unsigned(w));
@@ -541,7 +551,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
             }
             __syncwarp();
             // coalesced write-back of the chunk (float4 when aligned)
-            {
+            if (blocked) {
+                // four row segments of 8 texels: 8*N floats = 2*N float4 each, 16-byte aligned
+                const int perSeg = 2*N;
+                if (lane < 4*perSeg) {
+                    int seg = lane/perSeg, j = lane%perSeg;
+                    float *dst = P.out+s_g.outOffset+(size_t(blockOrigin)+size_t(seg)*w)*N;
+                    reinterpret_cast<float4 *>(dst)[j] = reinterpret_cast<const float4 *>(s_out[warp]+seg*8*N)[j];
+                }
+            } else {
                 unsigned nPix = tileEnd-chunkBase < 32u ? tileEnd-chunkBase : 32u;
                 int nFloats = int(nPix)*N;
                 float *dst = P.out+s_g.outOffset+size_t(chunkBase)*N;
