@@ -123,6 +123,20 @@ int b200msdf_generate(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shape,
 int b200msdf_generate_batch(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
                             int transform_per_glyph, const b200msdf_bitmap *outputs, const b200msdf_config *config);
 
+/* 8-bit atlas output (SURVEY.md §8f "next" #2): the same generation followed by a fused pixelFloatToByte
+ * (core/pixel-conversion.hpp:8-10) and placement store — every glyph's bytes land at its rectangle of the caller's atlas page
+ * (pixels + row_stride*y + N*x, row_stride in bytes).  When the destinations are pinned, device-accessible host memory the
+ * quantise kernel writes them directly; otherwise a packed byte buffer is copied back and scattered on the host.  The transfer
+ * is a quarter of the float path's. */
+typedef struct {
+    uint8_t *pixels;
+    int32_t width, height;
+    int32_t row_stride;                      /* bytes, may be negative */
+    int32_t y_downward;
+} b200msdf_bitmap_u8;
+int b200msdf_generate_batch_u8(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
+                               int transform_per_glyph, const b200msdf_bitmap_u8 *outputs, const b200msdf_config *config);
+
 /* msdfErrorCorrection(sdf, shape, transformation, config) on existing N-channel fields (N = 3 or 4), in place. */
 int b200msdf_error_correction(b200msdf_ctx *ctx, int channels, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
                               int transform_per_glyph, const b200msdf_bitmap *sdfs, const b200msdf_config *config);

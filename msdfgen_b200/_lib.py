@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("B200MSDF_LIB") or os.path.join(HERE, "libmsdfgen_b200
 EXPORTS = [
     "b200msdf_version", "b200msdf_last_error", "b200msdf_default_config", "b200msdf_create", "b200msdf_destroy",
     "b200msdf_set_stream", "b200msdf_synchronize", "b200msdf_launch_count", "b200msdf_host_alloc", "b200msdf_host_free",
-    "b200msdf_generate", "b200msdf_generate_batch", "b200msdf_error_correction", "b200msdf_fast_error_correction",
+    "b200msdf_generate", "b200msdf_generate_batch", "b200msdf_generate_batch_u8", "b200msdf_error_correction", "b200msdf_fast_error_correction",
     "b200msdf_batch_upload", "b200msdf_batch_upload_regions", "b200msdf_batch_launch", "b200msdf_batch_launch_stages", "b200msdf_batch_device_output", "b200msdf_batch_device_stencil",
     "b200msdf_batch_output_floats", "b200msdf_batch_glyph_offset", "b200msdf_batch_download", "b200msdf_batch_free",
 ]
@@ -36,6 +36,11 @@ class Transform(C.Structure):
 
 class Bitmap(C.Structure):
     _fields_ = [("pixels", C.POINTER(C.c_float)), ("width", C.c_int32), ("height", C.c_int32), ("row_stride", C.c_int32),
+                ("y_downward", C.c_int32)]
+
+
+class BitmapU8(C.Structure):
+    _fields_ = [("pixels", C.POINTER(C.c_uint8)), ("width", C.c_int32), ("height", C.c_int32), ("row_stride", C.c_int32),
                 ("y_downward", C.c_int32)]
 
 
@@ -73,6 +78,7 @@ def load():
     lib.b200msdf_host_free.restype = None
     lib.b200msdf_generate.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), C.POINTER(Bitmap), C.POINTER(Config)]
     lib.b200msdf_generate_batch.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(Bitmap), C.POINTER(Config)]
+    lib.b200msdf_generate_batch_u8.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(BitmapU8), C.POINTER(Config)]
     lib.b200msdf_error_correction.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(Bitmap), C.POINTER(Config)]
     lib.b200msdf_fast_error_correction.argtypes = [vp, i32, i32, C.POINTER(Transform), C.POINTER(Bitmap), C.c_double]
     lib.b200msdf_batch_upload.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(C.c_int32), i32,

@@ -185,6 +185,23 @@ class Context:
         _lib.check(self.lib.b200msdf_generate_batch(self.h, mode, C.byref(s), xf, per, bms, C.byref(cfg)))
         return outputs
 
+    def generate_batch_u8(self, mode, outputs, shapes: FlatShapes, transformations, config: MSDFGeneratorConfig = None, out_ydown=None):
+        """8-bit atlas output: outputs is a list of uint8[h,w,N] views (e.g. rectangles of one atlas page; row strides free)."""
+        config = config or MSDFGeneratorConfig()
+        xf, per = _transforms(transformations)
+        n = shapes.n_glyphs
+        bms = (_lib.BitmapU8 * max(n, 1))()
+        for g in range(n):
+            a = outputs[g]
+            h, w, ch = a.shape
+            assert a.dtype == np.uint8 and ch == CHANNELS[mode] and (a.size == 0 or (a.strides[2] == 1 and a.strides[1] == ch))
+            bms[g] = _lib.BitmapU8(a.ctypes.data_as(C.POINTER(C.c_uint8)), w, h, a.strides[0] if a.size else w * ch,
+                                   int(bool(out_ydown[g])) if out_ydown is not None else 0)
+        s = _shapes_struct(shapes)
+        cfg = config.c()
+        _lib.check(self.lib.b200msdf_generate_batch_u8(self.h, mode, C.byref(s), xf, per, bms, C.byref(cfg)))
+        return outputs
+
     def error_correction(self, sdfs, shapes: FlatShapes, transformations, config: MSDFGeneratorConfig = None, sdf_ydown=None, ec_buffer=None):
         config = config or MSDFGeneratorConfig()
         xf, per = _transforms(transformations)

@@ -93,13 +93,14 @@ struct b200msdf_batch {
     float *outOverride = nullptr;   // final texels go here instead of `out` (device-accessible pinned host memory of the caller)
     bool ecRan = false;
     DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, field, out, stencil, candidates, candCount;
+    DevBuf bytes, byteTargets;    // 8-bit output path
     DevBuf counters, scratch;     // per batch, so that batches launched on different streams never share scheduling state
     std::vector<GlyphDesc> hGlyphs;
     std::vector<TileDesc> hTiles;
     std::vector<int> hBig;
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
-        bigGlyphs.release(); bigRecs.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release();
+        bigGlyphs.release(); bigRecs.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); bytes.release(); byteTargets.release();
     }
 };
 
@@ -705,6 +706,84 @@ int b200msdf_generate_batch(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *
     if (rc) return rc;
     if (!direct)
         if ((rc = download_to_bitmaps(ctx, b, b->out.as<float>(), outputs))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200msdf_generate_batch_u8(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
+                               const b200msdf_bitmap_u8 *outputs, const b200msdf_config *config) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if ((rc = check_shapes(shapes))) return rc;
+    if ((rc = check_config(config))) return rc;
+    const int n = shapes->n_glyphs;
+    if (n == 0)
+        return 0;
+    if (!outputs)
+        return fail(B200MSDF_ERR_ARG, "null outputs");
+    if (mode < 1 || mode > 4)
+        return fail(B200MSDF_ERR_ARG, "mode %d out of range", mode);
+    const int N = channels_of(mode);
+    std::vector<int32_t> dims((size_t) n*2);
+    std::vector<uint8_t> yd((size_t) n);
+    bool direct = !getenv("B200MSDF_NO_ZEROCOPY");
+    for (int g = 0; g < n; ++g) {
+        if (outputs[g].width < 0 || outputs[g].height < 0 || ((size_t) outputs[g].width*outputs[g].height > 0 && !outputs[g].pixels))
+            return fail(B200MSDF_ERR_ARG, "bad output bitmap %d", g);
+        dims[2*(size_t) g] = outputs[g].width;
+        dims[2*(size_t) g+1] = outputs[g].height;
+        yd[(size_t) g] = outputs[g].y_downward != 0;
+    }
+    b200msdf_batch *b = &ctx->pool;
+    if ((rc = upload_batch(ctx, b, mode, shapes, xf, xfPerGlyph, dims.data(), 1, yd.data()))) return rc;
+    if ((rc = launch_batch(ctx, b, config))) return rc;
+    // destinations: the caller's rectangles when they are device-visible pinned memory, else a packed device buffer
+    std::vector<ByteTarget> targets((size_t) n);
+    for (int g = 0; g < n && direct; ++g) {
+        targets[(size_t) g].base = nullptr;
+        targets[(size_t) g].rowStride = 0;
+        if ((size_t) outputs[g].width*outputs[g].height == 0)
+            continue;
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, outputs[g].pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer) {
+            targets[(size_t) g].base = static_cast<uint8_t *>(attr.devicePointer);
+            targets[(size_t) g].rowStride = outputs[g].row_stride;
+        } else {
+            cudaGetLastError();
+            direct = false;
+        }
+    }
+    if (!direct) {
+        if ((rc = b->bytes.reserve(b->outFloats+64))) return rc;
+        for (int g = 0; g < n; ++g) {
+            targets[(size_t) g].base = b->bytes.as<uint8_t>()+b->hGlyphs[(size_t) g].outOffset;
+            targets[(size_t) g].rowStride = (long long) b->hGlyphs[(size_t) g].w*N;
+        }
+    }
+    if ((rc = b->byteTargets.reserve(sizeof(ByteTarget)*(size_t) n))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(b->byteTargets.p, targets.data(), sizeof(ByteTarget)*(size_t) n, cudaMemcpyHostToDevice, ctx->stream));
+    if (b->nTiles) {
+        int grid = b->nTiles < ctx->numSMs*8 ? b->nTiles : ctx->numSMs*8;
+        const float *src = b->out.as<float>();
+        switch (N) {
+            case 1: k4_quantize<1><<<grid, CTA_THREADS, 0, ctx->stream>>>(src, b->glyphs.as<GlyphDesc>(), b->tiles.as<TileDesc>(), b->nTiles, b->byteTargets.as<ByteTarget>()); break;
+            case 3: k4_quantize<3><<<grid, CTA_THREADS, 0, ctx->stream>>>(src, b->glyphs.as<GlyphDesc>(), b->tiles.as<TileDesc>(), b->nTiles, b->byteTargets.as<ByteTarget>()); break;
+            default: k4_quantize<4><<<grid, CTA_THREADS, 0, ctx->stream>>>(src, b->glyphs.as<GlyphDesc>(), b->tiles.as<TileDesc>(), b->nTiles, b->byteTargets.as<ByteTarget>()); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        ++ctx->launches;
+    }
+    if (!direct && b->outFloats) {
+        if ((rc = ctx->pinOut.reserve(b->outFloats))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ctx->pinOut.p, b->bytes.p, b->outFloats, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        const uint8_t *h = static_cast<const uint8_t *>(ctx->pinOut.p);
+        for (int g = 0; g < n; ++g) {
+            const GlyphDesc &d = b->hGlyphs[(size_t) g];
+            for (int r = 0; r < d.h; ++r)
+                memcpy(outputs[g].pixels+(ptrdiff_t) outputs[g].row_stride*r, h+d.outOffset+(size_t) r*d.w*N, (size_t) d.w*N);
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return 0;
 }

@@ -702,4 +702,36 @@ __global__ void __launch_bounds__(K3_THREADS) k3_exact_distance(KernelParams P) 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k4: fused 8-bit quantisation + atlas placement.  pixelFloatToByte (core/pixel-conversion.hpp:8-10) of every final float;
+// bytes go either to the glyph's rectangle in the caller's (pinned, device-visible) atlas page or to a packed byte buffer.
+struct ByteTarget {
+    uint8_t *base;          // first byte of row 0 in the caller's orientation (or packed buffer position)
+    long long rowStride;    // bytes
+};
+
+__device__ __forceinline__ uint8_t pixel_float_to_byte(float x) {
+    float c = x >= 0.f && x <= 1.f ? x : float(x > 0.f);       // clamp()
+    return (uint8_t) ~int(255.5f-255.f*c);
+}
+
+template <int N>
+__global__ void __launch_bounds__(CTA_THREADS) k4_quantize(const float *src, const GlyphDesc *glyphs, const TileDesc *tiles, int nTiles, const ByteTarget *targets) {
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        TileDesc td = tiles[tile];
+        GlyphDesc g = glyphs[td.glyph];
+        ByteTarget t = targets[td.glyph];
+        const unsigned total = unsigned(g.w)*unsigned(g.h);
+        unsigned tileEnd = td.pix0+TILE_PIXELS < total ? td.pix0+TILE_PIXELS : total;
+        for (unsigned i = td.pix0+threadIdx.x; i < tileEnd; i += CTA_THREADS) {
+            unsigned x = i%unsigned(g.w), row = i/unsigned(g.w);     // row in the caller's row order
+            const float *f = src+g.outOffset+size_t(i)*N;
+            uint8_t *d = t.base+t.rowStride*(long long) row+(long long) x*N;
+            #pragma unroll
+            for (int k = 0; k < N; ++k)
+                d[k] = pixel_float_to_byte(f[k]);
+        }
+    }
+}
+
 }  // namespace b200

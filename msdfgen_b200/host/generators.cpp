@@ -172,6 +172,35 @@ void generateMany(int mode, const std::vector<BitmapSection<float, N> > &outputs
 }
 
 template <int N>
+void generateManyBytes(int mode, const std::vector<BitmapSection<byte, N> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, bool overlapSupport, const ErrorCorrectionConfig *ec) {
+    b200msdf_ctx *ctx = context();
+    if (!ctx)
+        return;
+    if (outputs.size() != shapes.size() || (transformations.size() != shapes.size() && transformations.size() != 1)) {
+        std::fprintf(stderr, "msdfgen_b200: batch size mismatch (%zu outputs, %zu shapes, %zu transformations)\n", outputs.size(), shapes.size(), transformations.size());
+        std::abort();
+    }
+    FlatPool pool;
+    std::vector<b200msdf_bitmap_u8> bitmaps(outputs.size());
+    std::vector<b200msdf_transform> xf(transformations.size());
+    for (size_t i = 0; i < shapes.size(); ++i) {
+        pool.add(*shapes[i]);
+        bitmaps[i].pixels = outputs[i].pixels;
+        bitmaps[i].width = outputs[i].width; bitmaps[i].height = outputs[i].height;
+        bitmaps[i].row_stride = outputs[i].rowStride;
+        bitmaps[i].y_downward = outputs[i].yOrientation == Y_DOWNWARD;
+    }
+    for (size_t i = 0; i < transformations.size(); ++i)
+        xf[i] = marshal(transformations[i]);
+    b200msdf_shapes s = pool.view();
+    b200msdf_config c = marshal(overlapSupport, ec);
+    c.ec_buffer = NULL;
+    int rc = b200msdf_generate_batch_u8(ctx, mode, &s, xf.data(), transformations.size() > 1, bitmaps.data(), &c);
+    if (rc)
+        report(rc);
+}
+
+template <int N>
 void correctOne(const BitmapSection<float, N> &sdf, const Shape &shape, const SDFTransformation &transformation, const MSDFGeneratorConfig &config) {
     if (config.errorCorrection.mode == ErrorCorrectionConfig::DISABLED)
         return;
@@ -308,6 +337,18 @@ void generateSDFBatch(const std::vector<BitmapSection<float, 1> > &outputs, cons
 
 void generatePSDFBatch(const std::vector<BitmapSection<float, 1> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const GeneratorConfig &config) {
     generateMany(B200MSDF_PSDF, outputs, shapes, transformations, config.overlapSupport, NULL);
+}
+
+void generateSDFBatch(const std::vector<BitmapSection<byte, 1> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const GeneratorConfig &config) {
+    generateManyBytes(B200MSDF_SDF, outputs, shapes, transformations, config.overlapSupport, NULL);
+}
+
+void generateMSDFBatch(const std::vector<BitmapSection<byte, 3> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const MSDFGeneratorConfig &config) {
+    generateManyBytes(B200MSDF_MSDF, outputs, shapes, transformations, config.overlapSupport, &config.errorCorrection);
+}
+
+void generateMTSDFBatch(const std::vector<BitmapSection<byte, 4> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const MSDFGeneratorConfig &config) {
+    generateManyBytes(B200MSDF_MTSDF, outputs, shapes, transformations, config.overlapSupport, &config.errorCorrection);
 }
 
 }  // namespace b200

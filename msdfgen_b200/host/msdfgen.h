@@ -532,6 +532,11 @@ void generateMTSDFBatch(const std::vector<BitmapSection<float, 4> > &outputs, co
 void generateSDFBatch(const std::vector<BitmapSection<float, 1> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const GeneratorConfig &config = GeneratorConfig());
 void generatePSDFBatch(const std::vector<BitmapSection<float, 1> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const GeneratorConfig &config = GeneratorConfig());
 
+/// 8-bit atlas output: generation + fused pixelFloatToByte + placement into byte sections (e.g. rectangles of one atlas page).
+void generateSDFBatch(const std::vector<BitmapSection<byte, 1> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const GeneratorConfig &config = GeneratorConfig());
+void generateMSDFBatch(const std::vector<BitmapSection<byte, 3> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const MSDFGeneratorConfig &config = MSDFGeneratorConfig());
+void generateMTSDFBatch(const std::vector<BitmapSection<byte, 4> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const MSDFGeneratorConfig &config = MSDFGeneratorConfig());
+
 }  // namespace b200
 
 }  // namespace msdfgen

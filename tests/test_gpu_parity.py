@@ -301,3 +301,24 @@ def test_zero_copy_pinned_output_equals_copied_output(ctx):
         ctx.generate_batch(mode, pageable, atlas, xf)
         ctx.generate_batch(mode, pinned, atlas, xf)
         assert np.array_equal(pageable.view(np.uint32), np.asarray(pinned).view(np.uint32))
+
+
+def test_u8_atlas_output_equals_quantised_float_output(ctx, port):
+    """b200msdf_generate_batch_u8: fused pixelFloatToByte + placement into rectangles of an atlas page, for pageable pages
+    (packed device buffer + host scatter) and pinned pages (kernel writes the rectangles directly)."""
+    atlas = prep.prepare(synth_atlas(40, seed=4242))
+    xf = glyph_transform(32)
+    for mode in (api.SDF, api.MSDF, api.MTSDF):
+        n = api.CHANNELS[mode]
+        ref_f = np.empty((40, 32, 32, n), np.float32)
+        ctx.generate_batch(mode, ref_f, atlas, xf)
+        want = port.float_to_byte(ref_f)
+        assert np.array_equal(want, to_bytes(ref_f))
+        for pinned in (False, True):
+            page = ctx.pinned((5 * 36, 8 * 36 * n + 7), np.uint8) if pinned else np.empty((5 * 36, 8 * 36 * n + 7), np.uint8)
+            page[...] = 123
+            rects = [page[(g // 8) * 36 + 2:(g // 8) * 36 + 34, (g % 8) * 36 * n + 3:(g % 8) * 36 * n + 3 + 32 * n].reshape(32, 32, n) for g in range(40)]
+            ctx.generate_batch_u8(mode, rects, atlas, xf)
+            for g in range(40):
+                assert np.array_equal(rects[g], want[g]), (mode, pinned, g)
+            assert (np.asarray(page)[0:2] == 123).all() and (np.asarray(page)[:, :3] == 123).all()
