@@ -109,7 +109,7 @@ def cpu_reference(atlas, xf, size, sample_glyphs, mode="msdf"):
         gp.generate_batch(mode, warm.gbegin, warm.cbegin, warm.points, warm.orders, warm.colors, xf, size, size, glyph_parallel=True)
         _, t_glyph = gp.generate_batch(*args, glyph_parallel=True)
         # (b) the reference's own parallelisation: OpenMP over the rows of one bitmap (core/msdfgen.cpp:56-75)
-        few = atlas.slice(0, min(max(sample_glyphs // 32, 8), 64, atlas.n_glyphs))
+        few = atlas.slice(0, min(max(sample_glyphs // 64, 8), 32, atlas.n_glyphs))
         fargs = (mode, few.gbegin, few.cbegin, few.points, few.orders, few.colors, xf, size, size)
         _, t_rows = bindings.Oracle("reference_omp").generate_batch(*fargs, glyph_parallel=False)
         rows_rate = few.n_glyphs * size * size / t_rows
