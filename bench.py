@@ -135,18 +135,18 @@ def run_reference_arm(args, rank, world):
     atlas, xf = workload(args.glyphs, args.size, 0)
     sample = min(args.ref_sample, args.glyphs)
     for _ in range(min(args.warmup, 1)):
-        cpu_reference(atlas, xf, args.size, max(sample // 8, 8))
+        cpu_reference(atlas, xf, args.size, max(sample // 8, 8), args.mode)
     t_total, res = 0.0, None
     steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
-        res = cpu_reference(atlas, xf, args.size, sample)
+        res = cpu_reference(atlas, xf, args.size, sample, args.mode)
         t_total += res["seconds"]
     px = min(sample, atlas.n_glyphs) * args.size * args.size
     value = px * steps / t_total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
             "ms_per_step": 1e3 * t_total / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.glyphs} synthetic glyphs (8-64 mixed line/quadratic segments), msdf {args.size}x{args.size}, default MSDFGeneratorConfig (error correction on)",
+            "config": {"workload": f"{args.glyphs} synthetic glyphs (8-64 mixed line/quadratic segments), {args.mode} {args.size}x{args.size}, default MSDFGeneratorConfig (error correction on)",
                        "timed_sample_glyphs": min(sample, atlas.n_glyphs)},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -163,6 +163,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--glyphs", type=int, default=4096)
     ap.add_argument("--size", type=int, default=32)
+    ap.add_argument("--mode", default="msdf", choices=["sdf", "psdf", "msdf", "mtsdf"],
+                    help="generator (default msdf = the BASELINE metric; mtsdf --size 64 is BASELINE configs[2])")
     ap.add_argument("--ref-sample", type=int, default=4096, help="glyphs per reference-arm step")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="glyphs for the cpu_baseline leg of the b200 arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -199,7 +201,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    mode, channels = api.MSDF, 3
+    mode = {"sdf": api.SDF, "psdf": api.PSDF, "msdf": api.MSDF, "mtsdf": api.MTSDF}[args.mode]
+    channels = api.CHANNELS[mode]
     atlas, xf = workload(args.glyphs, args.size, rank)
     px_rank = atlas.n_glyphs * args.size * args.size
     cfg = api.MSDFGeneratorConfig()
@@ -296,7 +299,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"{args.glyphs} synthetic glyphs per GPU (8-64 mixed line/quadratic segments), msdf {args.size}x{args.size}, "
+            "config": {"workload": f"{args.glyphs} synthetic glyphs per GPU (8-64 mixed line/quadratic segments), {args.mode} {args.size}x{args.size}, "
                                    "default MSDFGeneratorConfig (overlap support + error correction EDGE_PRIORITY/CHECK_DISTANCE_AT_EDGE)",
                        "glyphs_per_gpu": args.glyphs, "segments_per_gpu": int(atlas.n_segments), "l2": "flushed between timed steps (512 MB memset)",
                        "parallelism": f"glyph sharding x{world}, no data-path collective"},
@@ -304,7 +307,7 @@ def main():
                     "api": "b200msdf_generate_batch (pinned host buffers in/out)"},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "wall_s": t_wall1 - t_wall0}
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        cb = cpu_reference(atlas, xf, args.size, args.cpu_sample)
+        cb = cpu_reference(atlas, xf, args.size, args.cpu_sample, args.mode)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if rank == 0:
         print(json.dumps(line))

@@ -379,10 +379,13 @@ __device__ __noinline__ Roots solve_cubic_normed(double a, double b, double c) {
 #ifndef B200_EXACT_ROOTS
 #define B200_EXACT_ROOTS 0
 #endif
+#ifndef B200_POLISH_STEPS
+#define B200_POLISH_STEPS 3
+#endif
 
 __device__ __noinline__ double cubic_polish(double t, double A, double B, double C) {
     #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < B200_POLISH_STEPS; ++i) {
         double f = fma(fma(t+A, t, B), t, C);
         double df = fma(fma(3.0, t, A+A), t, B);
         float rdf = __frcp_rn(float(df));
