@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200MSDF_VERSION 100 /* 0.1.0 */
+#define B200MSDF_VERSION 101 /* 0.1.1 */
 
 typedef enum {
     B200MSDF_OK = 0,
@@ -92,7 +92,18 @@ typedef struct {
     double min_improve_ratio;                /* default 1.11111111111111111 */
     uint8_t *ec_buffer;                      /* ErrorCorrectionConfig::buffer: optional, >= width*height bytes; single-shape calls
                                                 only; receives the stencil like the reference's does */
+    /* Scanline pass between generation and error correction — what the reference's command line does for `-scanline`
+     * (main.cpp:1223-1297: generate with error correction postponed, distanceSignCorrection, msdfErrorCorrection). */
+    int32_t scanline_pass;                   /* default 0 */
+    int32_t fill_rule;                       /* B200MSDF_FILL_*, default NONZERO */
+    float sdf_zero_value;                    /* default 0.5f */
 } b200msdf_config;
+
+/* FillRule, core/Scanline.h:9-14 */
+#define B200MSDF_FILL_NONZERO 0
+#define B200MSDF_FILL_ODD 1
+#define B200MSDF_FILL_POSITIVE 2
+#define B200MSDF_FILL_NEGATIVE 3
 
 typedef struct b200msdf_ctx b200msdf_ctx;       /* one per (thread, GPU): stream, pooled device + pinned buffers */
 typedef struct b200msdf_batch b200msdf_batch;   /* a shape batch resident in HBM with its output buffers */
@@ -145,6 +156,17 @@ int b200msdf_error_correction(b200msdf_ctx *ctx, int channels, const b200msdf_sh
 int b200msdf_fast_error_correction(b200msdf_ctx *ctx, int channels, int edge, const b200msdf_transform *transformation,
                                    const b200msdf_bitmap *sdf, double min_deviation_ratio);
 
+/* distanceSignCorrection(sdf, shape, projection, sdfZeroValue, fillRule) (core/rasterization.h:14-18, rasterization.cpp:19-108):
+ * makes the sign of every texel agree with the shape's scanline fill. channels 1, 3 or 4; in place; one field per glyph.
+ * Only the projection part of the transformations is used. */
+int b200msdf_sign_correction(b200msdf_ctx *ctx, int channels, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
+                             int transform_per_glyph, const b200msdf_bitmap *sdfs, float sdf_zero_value, int fill_rule);
+
+/* rasterize(output, shape, projection, fillRule) (core/rasterization.h:12, rasterization.cpp:9-17): 1.0f where the texel centre
+ * is filled, else 0.0f; outputs are 1-channel sections. */
+int b200msdf_rasterize(b200msdf_ctx *ctx, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
+                       int transform_per_glyph, const b200msdf_bitmap *outputs, int fill_rule);
+
 /* ---- HBM-resident batches (asynchronous on the context's stream) ---------------------------------------------------- */
 
 /* Uploads shapes + per-glyph geometry and allocates outputs. dims: [2] shared (w,h) or [2*n_glyphs] (dims_per_glyph != 0).
@@ -163,9 +185,13 @@ int b200msdf_batch_upload_regions(b200msdf_ctx *ctx, int mode, const b200msdf_sh
                                   int origins_per_glyph, b200msdf_batch **batch);
 /* Enqueues the whole path (contour windings -> distance field -> error correction) for the batch. */
 int b200msdf_batch_launch(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200msdf_config *config);
-/* Same, restricted to some stages (for per-kernel timing): bit 0 windings/prepare, bit 1 distance field, bit 2 error correction.
+/* Same, restricted to some stages (for per-kernel timing): bit 0 windings/prepare, bit 1 distance field, bit 2 error correction,
+ * bit 3 scanline pass (only when config->scanline_pass).
  * Later stages read what earlier stages of a previous full launch left in HBM. */
 int b200msdf_batch_launch_stages(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200msdf_config *config, unsigned stages);
+/* Sign-corrects the batch's most recent result in place on the device (after stages 1|2 it is the raw field, after a full
+ * launch the final output).  Not available for multi-channel region batches (the second sweep needs neighbouring tiles). */
+int b200msdf_batch_sign_correction(b200msdf_ctx *ctx, b200msdf_batch *batch, float sdf_zero_value, int fill_rule);
 float *b200msdf_batch_device_output(const b200msdf_batch *batch);      /* device pointer, valid until batch_free */
 uint8_t *b200msdf_batch_device_stencil(const b200msdf_batch *batch);   /* device pointer to per-texel EC flags (1 byte/texel) */
 size_t b200msdf_batch_output_floats(const b200msdf_batch *batch);      /* total floats incl. alignment padding */

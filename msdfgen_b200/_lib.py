@@ -17,6 +17,7 @@ EXPORTS = [
     "b200msdf_version", "b200msdf_last_error", "b200msdf_default_config", "b200msdf_create", "b200msdf_destroy",
     "b200msdf_set_stream", "b200msdf_synchronize", "b200msdf_launch_count", "b200msdf_host_alloc", "b200msdf_host_free",
     "b200msdf_generate", "b200msdf_generate_batch", "b200msdf_generate_batch_u8", "b200msdf_error_correction", "b200msdf_fast_error_correction",
+    "b200msdf_sign_correction", "b200msdf_rasterize", "b200msdf_batch_sign_correction",
     "b200msdf_batch_upload", "b200msdf_batch_upload_regions", "b200msdf_batch_launch", "b200msdf_batch_launch_stages", "b200msdf_batch_device_output", "b200msdf_batch_device_stencil",
     "b200msdf_batch_output_floats", "b200msdf_batch_glyph_offset", "b200msdf_batch_download", "b200msdf_batch_free",
 ]
@@ -46,7 +47,8 @@ class BitmapU8(C.Structure):
 
 class Config(C.Structure):
     _fields_ = [("overlap_support", C.c_int32), ("ec_mode", C.c_int32), ("ec_distance_check_mode", C.c_int32),
-                ("min_deviation_ratio", C.c_double), ("min_improve_ratio", C.c_double), ("ec_buffer", C.POINTER(C.c_uint8))]
+                ("min_deviation_ratio", C.c_double), ("min_improve_ratio", C.c_double), ("ec_buffer", C.POINTER(C.c_uint8)),
+                ("scanline_pass", C.c_int32), ("fill_rule", C.c_int32), ("sdf_zero_value", C.c_float)]
 
 
 _lib = None
@@ -81,6 +83,9 @@ def load():
     lib.b200msdf_generate_batch_u8.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(BitmapU8), C.POINTER(Config)]
     lib.b200msdf_error_correction.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(Bitmap), C.POINTER(Config)]
     lib.b200msdf_fast_error_correction.argtypes = [vp, i32, i32, C.POINTER(Transform), C.POINTER(Bitmap), C.c_double]
+    lib.b200msdf_sign_correction.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(Bitmap), C.c_float, i32]
+    lib.b200msdf_rasterize.argtypes = [vp, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(Bitmap), i32]
+    lib.b200msdf_batch_sign_correction.argtypes = [vp, vp, C.c_float, i32]
     lib.b200msdf_batch_upload.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(C.c_int32), i32,
                                           C.POINTER(C.c_uint8), C.POINTER(vp)]
     lib.b200msdf_batch_upload_regions.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(C.c_int32), i32,

@@ -20,6 +20,7 @@ CHANNELS = {SDF: 1, PSDF: 1, MSDF: 3, MTSDF: 4}
 EC_DISABLED, EC_INDISCRIMINATE, EC_EDGE_PRIORITY, EC_EDGE_ONLY = 0, 1, 2, 3
 DCM_DO_NOT_CHECK, DCM_CHECK_AT_EDGE, DCM_ALWAYS_CHECK = 0, 1, 2
 DEFAULT_RATIO = 1.11111111111111111
+FILL_NONZERO, FILL_ODD, FILL_POSITIVE, FILL_NEGATIVE = 0, 1, 2, 3     # FillRule, core/Scanline.h:9-14
 
 
 @dataclass
@@ -36,6 +37,10 @@ class MSDFGeneratorConfig:
     """core/generator-config.h:49-64 (GeneratorConfig + errorCorrection)"""
     overlapSupport: bool = True
     errorCorrection: ErrorCorrectionConfig = None
+    # extension: the command line's scanline pass (main.cpp:1223-1297) run on the device between generation and error correction
+    scanlinePass: bool = False
+    fillRule: int = FILL_NONZERO
+    sdfZeroValue: float = 0.5
 
     def __post_init__(self):
         if self.errorCorrection is None:
@@ -43,7 +48,8 @@ class MSDFGeneratorConfig:
 
     def c(self, ec_buffer=None):
         cfg = _lib.Config(int(self.overlapSupport), self.errorCorrection.mode, self.errorCorrection.distanceCheckMode,
-                          self.errorCorrection.minDeviationRatio, self.errorCorrection.minImproveRatio, None)
+                          self.errorCorrection.minDeviationRatio, self.errorCorrection.minImproveRatio, None,
+                          int(self.scanlinePass), int(self.fillRule), float(self.sdfZeroValue))
         if ec_buffer is not None:
             cfg.ec_buffer = ec_buffer.ctypes.data_as(C.POINTER(C.c_uint8))
         return cfg
@@ -74,7 +80,12 @@ def _transforms(xf):
     """Accepts SDFTransformation | array[6] | array[n,6] (sx, sy, tx, ty, range_lower, range_upper) -> (ctypes array, per_glyph)."""
     if isinstance(xf, SDFTransformation):
         return (_lib.Transform * 1)(xf.c()), 0
-    a = np.asarray(xf, dtype=np.float64).reshape(-1, 6)
+    a = np.asarray(xf, dtype=np.float64)
+    if (a.ndim == 1 and a.size == 4) or (a.ndim == 2 and a.shape[1] == 4):
+        # projection only (scanline passes): any distance range will do
+        a = a.reshape(-1, 4)
+        a = np.concatenate([a, np.tile([-1.0, 1.0], (len(a), 1))], axis=1)
+    a = a.reshape(-1, 6)
     arr = (_lib.Transform * len(a))()
     for i, r in enumerate(a):
         arr[i] = SDFTransformation.from_array(r).c()
@@ -218,6 +229,22 @@ class Context:
         _lib.check(self.lib.b200msdf_fast_error_correction(self.h, sdf.shape[2], int(edge), xf, C.byref(bm), min_deviation_ratio))
         return sdf
 
+    def sign_correction(self, sdfs, shapes: FlatShapes, transformations, sdf_zero_value=0.5, fill_rule=FILL_NONZERO, sdf_ydown=None):
+        """distanceSignCorrection (core/rasterization.h:14-18) on every [h,w,N] field of the list, in place."""
+        xf, per = _transforms(transformations)
+        bms = _bitmaps(sdfs, shapes.n_glyphs, sdf_ydown)
+        s = _shapes_struct(shapes)
+        _lib.check(self.lib.b200msdf_sign_correction(self.h, sdfs[0].shape[2], C.byref(s), xf, per, bms, sdf_zero_value, fill_rule))
+        return sdfs
+
+    def rasterize(self, outputs, shapes: FlatShapes, transformations, fill_rule=FILL_NONZERO, out_ydown=None):
+        """rasterize (core/rasterization.h:12) into every [h,w,1] output of the list."""
+        xf, per = _transforms(transformations)
+        bms = _bitmaps(outputs, shapes.n_glyphs, out_ydown)
+        s = _shapes_struct(shapes)
+        _lib.check(self.lib.b200msdf_rasterize(self.h, C.byref(s), xf, per, bms, fill_rule))
+        return outputs
+
     # ---- HBM-resident batches --------------------------------------------------------------------------------------
     def upload(self, mode, shapes: FlatShapes, transformations, dims, out_ydown=None, origins=None):
         """origins: (x0, y0) pixel origin(s) of the output block(s) inside their full image (region batches, SDF/PSDF or EC off)."""
@@ -248,11 +275,15 @@ class Batch:
         _lib.check(self.ctx.lib.b200msdf_batch_launch(self.ctx.h, self.h, C.byref(cfg)))
 
     def launch_stages(self, stages, config: MSDFGeneratorConfig = None):
-        """stages: bit 0 windings/prepare, bit 1 distance field, bit 2 error correction (per-kernel timing)."""
+        """stages: bit 0 windings/prepare, bit 1 distance field, bit 2 error correction, bit 3 scanline pass (per-kernel timing)."""
         cfg = (config or MSDFGeneratorConfig()).c()
         _lib.check(self.ctx.lib.b200msdf_batch_launch_stages(self.ctx.h, self.h, C.byref(cfg), stages))
 
     @property
+    def sign_correction(self, sdf_zero_value=0.5, fill_rule=FILL_NONZERO):
+        """distanceSignCorrection on the batch's most recent device result, in place."""
+        _lib.check(self.ctx.lib.b200msdf_batch_sign_correction(self.ctx.h, self.h, sdf_zero_value, fill_rule))
+
     def output_floats(self):
         return int(self.ctx.lib.b200msdf_batch_output_floats(self.h))
 
@@ -318,6 +349,16 @@ def generateMTSDF(output, shape, transformation, config=None, **kw):
 
 def msdfErrorCorrection(sdf, shape, transformation, config=None, **kw):
     return default_context().error_correction([sdf], shape, transformation, config, **kw)[0]
+
+
+def distanceSignCorrection(sdf, shape, projection, sdfZeroValue=0.5, fillRule=FILL_NONZERO, **kw):
+    """core/rasterization.h:14-18; `projection` may be a Projection-like (scale, translate) pair or an SDFTransformation."""
+    return default_context().sign_correction([sdf], shape, projection, sdfZeroValue, fillRule, **kw)[0]
+
+
+def rasterize(output, shape, projection, fillRule=FILL_NONZERO, **kw):
+    """core/rasterization.h:12"""
+    return default_context().rasterize([output], shape, projection, fillRule, **kw)[0]
 
 
 def msdfFastDistanceErrorCorrection(sdf, transformation, minDeviationRatio=DEFAULT_RATIO):

@@ -3,6 +3,7 @@
 // kernels.cuh or fails.
 #include "../../include/msdfgen_b200.h"
 #include "error_correction.cuh"
+#include "scanline.cuh"
 
 #include <climits>
 #include <cstdarg>
@@ -92,6 +93,7 @@ struct b200msdf_batch {
     bool regions = false;
     float *outOverride = nullptr;   // final texels go here instead of `out` (device-accessible pinned host memory of the caller)
     bool ecRan = false;
+    float *current = nullptr;       // device pointer to the most recent result (raw field after k1, final output after a full launch)
     DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, field, out, stencil, candidates, candCount;
     DevBuf bytes, byteTargets;    // 8-bit output path
     DevBuf counters, scratch;     // per batch, so that batches launched on different streams never share scheduling state
@@ -408,10 +410,42 @@ int check_config(const b200msdf_config *cfg) {
         return fail(B200MSDF_ERR_ARG, "null config");
     if (cfg->ec_mode < 0 || cfg->ec_mode > 3 || cfg->ec_distance_check_mode < 0 || cfg->ec_distance_check_mode > 2)
         return fail(B200MSDF_ERR_ARG, "error-correction mode out of range");
+    if (cfg->scanline_pass && (cfg->fill_rule < 0 || cfg->fill_rule > 3))
+        return fail(B200MSDF_ERR_ARG, "fill rule out of range");
     return 0;
 }
 
-int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cfg, unsigned stages = 7u) {
+// distanceSignCorrection over every glyph of the batch: src -> dst (device pointers in the batch's output layout; may alias).
+int launch_sign(b200msdf_ctx *ctx, b200msdf_batch *b, KernelParams &P, const float *src, float *dst, float zero, int fillRule) {
+    if (fillRule < 0 || fillRule > 3)
+        return fail(B200MSDF_ERR_ARG, "fill rule out of range");
+    if (b->nTiles == 0)
+        return 0;
+    if (b->N >= 3 && b->regions)
+        return fail(B200MSDF_ERR_ARG, "multi-channel sign correction is not available for region batches (needs neighbouring tiles)");
+    int *ambiguous = b->counters.as<int>()+8;
+    int8_t *match = b->N >= 3 ? b->stencil.as<int8_t>() : nullptr;
+    if (b->N >= 3)
+        CUDA_TRY(cudaMemsetAsync(ambiguous, 0, sizeof(int), ctx->stream));
+    switch (b->N) {
+        case 1: k5_scanline_sign<1><<<b->nTiles, CTA_THREADS, 0, ctx->stream>>>(P, src, dst, match, ambiguous, zero, fillRule); break;
+        case 3: k5_scanline_sign<3><<<b->nTiles, CTA_THREADS, 0, ctx->stream>>>(P, src, dst, match, ambiguous, zero, fillRule); break;
+        default: k5_scanline_sign<4><<<b->nTiles, CTA_THREADS, 0, ctx->stream>>>(P, src, dst, match, ambiguous, zero, fillRule); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    ++ctx->launches;
+    if (b->N >= 3) {
+        if (b->N == 3)
+            k5_resolve_ambiguous<3><<<b->nTiles, CTA_THREADS, 0, ctx->stream>>>(P, dst, match, ambiguous, zero);
+        else
+            k5_resolve_ambiguous<4><<<b->nTiles, CTA_THREADS, 0, ctx->stream>>>(P, dst, match, ambiguous, zero);
+        CUDA_TRY(cudaGetLastError());
+        ++ctx->launches;
+    }
+    return 0;
+}
+
+int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cfg, unsigned stages = 15u) {
     int rc = check_config(cfg);
     if (rc) return rc;
     if (b->nGlyphs == 0 || b->nTiles == 0) {
@@ -424,7 +458,10 @@ int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
     if (ec && b->regions)
         return fail(B200MSDF_ERR_ARG, "error correction is not available for region batches (needs neighbouring tiles): disable it or generate whole images");
     float *finalOut = b->outOverride ? b->outOverride : b->out.as<float>();
-    P.field = ec ? b->field.as<float>() : finalOut;
+    const bool scan = cfg->scanline_pass != 0;
+    // k1's target: the field buffer when error correction follows; otherwise the final output — except that a scanline pass
+    // in front of caller-owned (zero-copy) memory reads device memory and makes the final store itself
+    P.field = ec ? b->field.as<float>() : scan ? b->out.as<float>() : finalOut;
     P.out = finalOut;
     P.stencil = ec ? b->stencil.as<uint8_t>() : nullptr;
     if (stages&1u)
@@ -435,8 +472,15 @@ int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
     }
     if (stages&2u)
         if ((rc = launch_k1(ctx, b->mode, cfg->overlap_support != 0, P, b->maxContours))) return rc;
-    if (ec && (stages&4u))
+    b->current = P.field;
+    if (scan && (stages&8u))
+        if ((rc = launch_sign(ctx, b, P, P.field, ec ? P.field : finalOut, cfg->sdf_zero_value, cfg->fill_rule))) return rc;
+    if (scan && !ec)
+        b->current = finalOut;
+    if (ec && (stages&4u)) {
         if ((rc = launch_k2(ctx, b, b->N, cfg->overlap_support != 0, P, b->maxContours))) return rc;
+        b->current = finalOut;
+    }
     b->launched = true;
     b->ecRan = ec;
     return 0;
@@ -516,6 +560,9 @@ void b200msdf_default_config(b200msdf_config *cfg) {
     cfg->min_deviation_ratio = 1.11111111111111111;
     cfg->min_improve_ratio = 1.11111111111111111;
     cfg->ec_buffer = nullptr;
+    cfg->scanline_pass = 0;
+    cfg->fill_rule = B200MSDF_FILL_NONZERO;
+    cfg->sdf_zero_value = .5f;
 }
 
 int b200msdf_create(int device, b200msdf_ctx **out) {
@@ -866,6 +913,78 @@ int b200msdf_fast_error_correction(b200msdf_ctx *ctx, int channels, int edge, co
     cfg.ec_distance_check_mode = B200MSDF_DCM_DO_NOT_CHECK;
     cfg.min_deviation_ratio = min_deviation_ratio;
     return ec_common(ctx, channels, &empty, xf, 0, sdf, &cfg, 1);
+}
+
+// Host-buffer scanline passes: upload, gather the caller's fields (sign correction), run, scatter back.
+static int scanline_common(b200msdf_ctx *ctx, int channels, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
+                           const b200msdf_bitmap *bitmaps, float zero, int fillRule, bool rasterizeOnly) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (channels != 1 && channels != 3 && channels != 4)
+        return fail(B200MSDF_ERR_ARG, "sign correction needs 1, 3 or 4 channels");
+    if (fillRule < 0 || fillRule > 3)
+        return fail(B200MSDF_ERR_ARG, "fill rule out of range");
+    if ((rc = check_shapes(shapes))) return rc;
+    if ((rc = check_bitmaps(bitmaps, shapes->n_glyphs))) return rc;
+    if (shapes->n_glyphs == 0)
+        return 0;
+    std::vector<int32_t> dims;
+    std::vector<uint8_t> yd;
+    dims_from_bitmaps(bitmaps, shapes->n_glyphs, dims, yd);
+    b200msdf_batch *b = &ctx->pool;
+    int mode = channels == 1 ? B200MSDF_SDF : channels == 3 ? B200MSDF_MSDF : B200MSDF_MTSDF;
+    if ((rc = upload_batch(ctx, b, mode, shapes, xf, xfPerGlyph, dims.data(), 1, yd.data()))) return rc;
+    if (b->nTiles == 0)
+        return 0;
+    b200msdf_config cfg;
+    b200msdf_default_config(&cfg);
+    KernelParams P;
+    fill_params(ctx, b, &cfg, P);
+    float *dev = b->out.as<float>();
+    if (rasterizeOnly) {
+        k5_rasterize<<<b->nTiles, CTA_THREADS, 0, ctx->stream>>>(P, dev, fillRule);
+        CUDA_TRY(cudaGetLastError());
+        ++ctx->launches;
+    } else {
+        if ((rc = ctx->pinIn.reserve(b->outFloats*4))) return rc;
+        float *h = static_cast<float *>(ctx->pinIn.p);
+        for (int g = 0; g < b->nGlyphs; ++g) {
+            const GlyphDesc &d = b->hGlyphs[(size_t) g];
+            for (int r = 0; r < d.h; ++r)
+                memcpy(h+d.outOffset+(size_t) r*d.w*channels, bitmaps[g].pixels+(ptrdiff_t) bitmaps[g].row_stride*r, sizeof(float)*(size_t) d.w*channels);
+        }
+        CUDA_TRY(cudaMemcpyAsync(dev, h, b->outFloats*4, cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = launch_sign(ctx, b, P, dev, dev, zero, fillRule))) return rc;
+    }
+    if ((rc = download_to_bitmaps(ctx, b, dev, bitmaps))) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int b200msdf_sign_correction(b200msdf_ctx *ctx, int channels, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
+                             const b200msdf_bitmap *sdfs, float sdf_zero_value, int fill_rule) {
+    return scanline_common(ctx, channels, shapes, xf, xfPerGlyph, sdfs, sdf_zero_value, fill_rule, false);
+}
+
+int b200msdf_rasterize(b200msdf_ctx *ctx, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
+                       const b200msdf_bitmap *outputs, int fill_rule) {
+    return scanline_common(ctx, 1, shapes, xf, xfPerGlyph, outputs, 0.f, fill_rule, true);
+}
+
+int b200msdf_batch_sign_correction(b200msdf_ctx *ctx, b200msdf_batch *batch, float sdf_zero_value, int fill_rule) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!batch)
+        return fail(B200MSDF_ERR_ARG, "null batch");
+    if (!batch->launched || !batch->current)
+        return fail(B200MSDF_ERR_ARG, "the batch has no result yet: launch it first");
+    if (batch->nTiles == 0)
+        return 0;
+    b200msdf_config cfg;
+    b200msdf_default_config(&cfg);
+    KernelParams P;
+    fill_params(ctx, batch, &cfg, P);
+    return launch_sign(ctx, batch, P, batch->current, batch->current, sdf_zero_value, fill_rule);
 }
 
 int b200msdf_batch_upload(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,

@@ -115,6 +115,9 @@ b200msdf_bitmap marshal(const BitmapSection<float, N> &b) {
     return m;
 }
 
+struct ScanlinePass { bool enabled; int fillRule; float zero; };
+thread_local ScanlinePass g_scanline = { false, 0, .5f };
+
 b200msdf_config marshal(bool overlapSupport, const ErrorCorrectionConfig *ec) {
     b200msdf_config c;
     b200msdf_default_config(&c);
@@ -166,6 +169,9 @@ void generateMany(int mode, const std::vector<BitmapSection<float, N> > &outputs
     b200msdf_shapes s = pool.view();
     b200msdf_config c = marshal(overlapSupport, ec);
     c.ec_buffer = NULL;
+    c.scanline_pass = g_scanline.enabled;
+    c.fill_rule = g_scanline.fillRule;
+    c.sdf_zero_value = g_scanline.zero;
     int rc = b200msdf_generate_batch(ctx, mode, &s, xf.data(), transformations.size() > 1, bitmaps.data(), &c);
     if (rc)
         report(rc);
@@ -195,6 +201,9 @@ void generateManyBytes(int mode, const std::vector<BitmapSection<byte, N> > &out
     b200msdf_shapes s = pool.view();
     b200msdf_config c = marshal(overlapSupport, ec);
     c.ec_buffer = NULL;
+    c.scanline_pass = g_scanline.enabled;
+    c.fill_rule = g_scanline.fillRule;
+    c.sdf_zero_value = g_scanline.zero;
     int rc = b200msdf_generate_batch_u8(ctx, mode, &s, xf.data(), transformations.size() > 1, bitmaps.data(), &c);
     if (rc)
         report(rc);
@@ -226,6 +235,21 @@ void correctShapeless(const BitmapSection<float, N> &sdf, const SDFTransformatio
     b200msdf_transform t = marshal(transformation);
     b200msdf_bitmap b = marshal(sdf);
     int rc = b200msdf_fast_error_correction(ctx, N, edge ? 1 : 0, &t, &b, minDeviationRatio);
+    if (rc)
+        report(rc);
+}
+
+template <int N>
+void signCorrectOne(const BitmapSection<float, N> &sdf, const Shape &shape, const Projection &projection, float sdfZeroValue, FillRule fillRule) {
+    b200msdf_ctx *ctx = context();
+    if (!ctx)
+        return;
+    FlatPool pool;
+    pool.add(shape);
+    b200msdf_shapes s = pool.view();
+    b200msdf_transform t = marshal(SDFTransformation(projection, Range(1)));
+    b200msdf_bitmap b = marshal(sdf);
+    int rc = b200msdf_sign_correction(ctx, N, &s, &t, 0, &b, sdfZeroValue, (int) fillRule);
     if (rc)
         report(rc);
 }
@@ -311,6 +335,34 @@ void msdfFastEdgeErrorCorrection(const BitmapSection<float, 4> &sdf, const Proje
 void msdfFastEdgeErrorCorrection(const BitmapSection<float, 3> &sdf, Range pxRange, double minDeviationRatio) { correctShapeless(sdf, SDFTransformation(Projection(), pxRange), minDeviationRatio, true); }
 void msdfFastEdgeErrorCorrection(const BitmapSection<float, 4> &sdf, Range pxRange, double minDeviationRatio) { correctShapeless(sdf, SDFTransformation(Projection(), pxRange), minDeviationRatio, true); }
 
+// ---- scanline pass ---------------------------------------------------------------------------------------------------------
+
+void rasterize(BitmapSection<float, 1> output, const Shape &shape, const Projection &projection, FillRule fillRule) {
+    b200msdf_ctx *ctx = context();
+    if (!ctx)
+        return;
+    FlatPool pool;
+    pool.add(shape);
+    b200msdf_shapes s = pool.view();
+    b200msdf_transform t = marshal(SDFTransformation(projection, Range(1)));
+    b200msdf_bitmap b = marshal(output);
+    int rc = b200msdf_rasterize(ctx, &s, &t, 0, &b, (int) fillRule);
+    if (rc)
+        report(rc);
+}
+
+void distanceSignCorrection(BitmapSection<float, 1> sdf, const Shape &shape, const Projection &projection, float sdfZeroValue, FillRule fillRule) { signCorrectOne(sdf, shape, projection, sdfZeroValue, fillRule); }
+void distanceSignCorrection(BitmapSection<float, 3> sdf, const Shape &shape, const Projection &projection, float sdfZeroValue, FillRule fillRule) { signCorrectOne(sdf, shape, projection, sdfZeroValue, fillRule); }
+void distanceSignCorrection(BitmapSection<float, 4> sdf, const Shape &shape, const Projection &projection, float sdfZeroValue, FillRule fillRule) { signCorrectOne(sdf, shape, projection, sdfZeroValue, fillRule); }
+
+void rasterize(const BitmapSection<float, 1> &output, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule) { rasterize(output, shape, Projection(scale, translate), fillRule); }
+void distanceSignCorrection(BitmapSection<float, 1> sdf, const Shape &shape, const Projection &projection, FillRule fillRule) { signCorrectOne(sdf, shape, projection, .5f, fillRule); }
+void distanceSignCorrection(BitmapSection<float, 3> sdf, const Shape &shape, const Projection &projection, FillRule fillRule) { signCorrectOne(sdf, shape, projection, .5f, fillRule); }
+void distanceSignCorrection(BitmapSection<float, 4> sdf, const Shape &shape, const Projection &projection, FillRule fillRule) { signCorrectOne(sdf, shape, projection, .5f, fillRule); }
+void distanceSignCorrection(const BitmapSection<float, 1> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule) { signCorrectOne(sdf, shape, Projection(scale, translate), .5f, fillRule); }
+void distanceSignCorrection(const BitmapSection<float, 3> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule) { signCorrectOne(sdf, shape, Projection(scale, translate), .5f, fillRule); }
+void distanceSignCorrection(const BitmapSection<float, 4> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule) { signCorrectOne(sdf, shape, Projection(scale, translate), .5f, fillRule); }
+
 // ---- B200 additions --------------------------------------------------------------------------------------------------------
 
 namespace b200 {
@@ -321,6 +373,12 @@ ErrorHandler setErrorHandler(ErrorHandler handler) {
     ErrorHandler prev = g_handler;
     g_handler = handler;
     return prev;
+}
+
+void setScanlinePass(bool enabled, FillRule fillRule, float sdfZeroValue) {
+    g_scanline.enabled = enabled;
+    g_scanline.fillRule = (int) fillRule;
+    g_scanline.zero = sdfZeroValue;
 }
 
 void generateMSDFBatch(const std::vector<BitmapSection<float, 3> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const MSDFGeneratorConfig &config) {

@@ -516,6 +516,31 @@ void msdfFastEdgeErrorCorrection(const BitmapSection<float, 3> &sdf, Range pxRan
 void msdfFastEdgeErrorCorrection(const BitmapSection<float, 4> &sdf, Range pxRange, double minDeviationRatio = ErrorCorrectionConfig::defaultMinDeviationRatio);
 
 // ---- B200 additions: atlas-sized batches and device control ------------------------------------------------------------------
+// ---- scanline pass (core/Scanline.h:9-14, core/rasterization.h) -----------------------------------------------------
+
+/// Fill rule dictates how intersection total is interpreted during rasterization.
+enum FillRule {
+    FILL_NONZERO,
+    FILL_ODD, // "even-odd"
+    FILL_POSITIVE,
+    FILL_NEGATIVE
+};
+
+/// Rasterizes the shape into a monochrome bitmap.
+void rasterize(BitmapSection<float, 1> output, const Shape &shape, const Projection &projection, FillRule fillRule = FILL_NONZERO);
+/// Fixes the sign of the input signed distance field, so that it matches the shape's rasterized fill.
+void distanceSignCorrection(BitmapSection<float, 1> sdf, const Shape &shape, const Projection &projection, float sdfZeroValue = .5f, FillRule fillRule = FILL_NONZERO);
+void distanceSignCorrection(BitmapSection<float, 3> sdf, const Shape &shape, const Projection &projection, float sdfZeroValue = .5f, FillRule fillRule = FILL_NONZERO);
+void distanceSignCorrection(BitmapSection<float, 4> sdf, const Shape &shape, const Projection &projection, float sdfZeroValue = .5f, FillRule fillRule = FILL_NONZERO);
+// Old versions of the function API's kept for backwards compatibility
+void rasterize(const BitmapSection<float, 1> &output, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule = FILL_NONZERO);
+void distanceSignCorrection(BitmapSection<float, 1> sdf, const Shape &shape, const Projection &projection, FillRule fillRule);
+void distanceSignCorrection(BitmapSection<float, 3> sdf, const Shape &shape, const Projection &projection, FillRule fillRule);
+void distanceSignCorrection(BitmapSection<float, 4> sdf, const Shape &shape, const Projection &projection, FillRule fillRule);
+void distanceSignCorrection(const BitmapSection<float, 1> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule = FILL_NONZERO);
+void distanceSignCorrection(const BitmapSection<float, 3> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule = FILL_NONZERO);
+void distanceSignCorrection(const BitmapSection<float, 4> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule = FILL_NONZERO);
+
 namespace b200 {
 
 /// Selects the CUDA device used by the calling thread's generator context (default 0).
@@ -531,6 +556,11 @@ void generateMSDFBatch(const std::vector<BitmapSection<float, 3> > &outputs, con
 void generateMTSDFBatch(const std::vector<BitmapSection<float, 4> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const MSDFGeneratorConfig &config = MSDFGeneratorConfig());
 void generateSDFBatch(const std::vector<BitmapSection<float, 1> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const GeneratorConfig &config = GeneratorConfig());
 void generatePSDFBatch(const std::vector<BitmapSection<float, 1> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const GeneratorConfig &config = GeneratorConfig());
+
+/// The command line's -scanline flow for a whole batch in ONE device pass: generation with error correction postponed,
+/// distanceSignCorrection, then msdfErrorCorrection (main.cpp:1223-1297).  Applies to the Batch calls of the calling thread
+/// made while enabled.
+void setScanlinePass(bool enabled, FillRule fillRule = FILL_NONZERO, float sdfZeroValue = .5f);
 
 /// 8-bit atlas output: generation + fused pixelFloatToByte + placement into byte sections (e.g. rectangles of one atlas page).
 void generateSDFBatch(const std::vector<BitmapSection<byte, 1> > &outputs, const std::vector<const Shape *> &shapes, const std::vector<SDFTransformation> &transformations, const GeneratorConfig &config = GeneratorConfig());

@@ -209,6 +209,34 @@ class Oracle:
             raise RuntimeError("fast_error_correction failed")
         return sdf
 
+    def sign_correction(self, sdf, cbegin, points, orders, xf, zero_value=0.5, fill_rule=0, shape_ydown=False, sdf_ydown=False):
+        """distanceSignCorrection (core/rasterization.h) on a copy of sdf[h,w,N]; fill_rule 0 NONZERO 1 ODD 2 POSITIVE 3 NEGATIVE."""
+        sdf = np.array(sdf, dtype=np.float32, order="C", copy=True)
+        h, w, n = sdf.shape
+        cbegin, points, orders = _u32(cbegin), _f64(points), _u8(orders)
+        x = _f64(xf).reshape(-1)[:4].copy()
+        fn = getattr(self.lib, self.pfx + "sign_correction")
+        fn.restype = C.c_int
+        rc = fn(C.c_int(n), C.c_int(len(cbegin) - 1), _p(cbegin, C.c_uint32), _p(points, C.c_double), _p(orders, C.c_uint8), None,
+                C.c_int(int(shape_ydown)), _p(x, C.c_double), _p(sdf, C.c_float), C.c_int(w), C.c_int(h), C.c_int(w * n),
+                C.c_int(int(sdf_ydown)), C.c_float(zero_value), C.c_int(fill_rule))
+        if rc:
+            raise RuntimeError("sign_correction failed")
+        return sdf
+
+    def rasterize(self, cbegin, points, orders, xf, w, h, fill_rule=0, shape_ydown=False, out_ydown=False):
+        """rasterize (core/rasterization.h) -> float32 [h,w,1] of 0/1."""
+        out = np.zeros((h, w, 1), np.float32)
+        cbegin, points, orders = _u32(cbegin), _f64(points), _u8(orders)
+        x = _f64(xf).reshape(-1)[:4].copy()
+        fn = getattr(self.lib, self.pfx + "rasterize")
+        fn.restype = C.c_int
+        rc = fn(C.c_int(len(cbegin) - 1), _p(cbegin, C.c_uint32), _p(points, C.c_double), _p(orders, C.c_uint8), C.c_int(int(shape_ydown)),
+                _p(x, C.c_double), _p(out, C.c_float), C.c_int(w), C.c_int(h), C.c_int(int(out_ydown)), C.c_int(fill_rule))
+        if rc:
+            raise RuntimeError("rasterize failed")
+        return out
+
     # -- pieces ------------------------------------------------------------------------------------------------------
     def distance(self, mode, overlap, cbegin, points, orders, colors, pts):
         """Raw fp64 shape distance (oneShotDistance) at arbitrary points -> float64[nPts, N]."""

@@ -1037,6 +1037,229 @@ int oracle_generate_batch(int mode, int nGlyphs, const uint32_t *gbegin, const u
     return 0;
 }
 
+/* ---- scanline sign correction (core/rasterization.cpp:19-96, Scanline.cpp, edge-segments.cpp:279-403) ---- */
+static int isign(double n) { return (0 < n)-(n < 0); }
+
+/* {Linear,Quadratic,Cubic}Segment::scanlineIntersections: x positions and crossing directions of the edge on the line y */
+static int seg_scanline(int order, const v2 *p, double x[3], int dy[3], double y) {
+    if (order == 1) {   /* edge-segments.cpp:279-287 */
+        if ((y >= p[0].y && y < p[1].y) || (y >= p[1].y && y < p[0].y)) {
+            double param = (y-p[0].y)/(p[1].y-p[0].y);
+            x[0] = (1.0-param)*p[0].x+param*p[1].x;
+            dy[0] = isign(p[1].y-p[0].y);
+            return 1;
+        }
+        return 0;
+    }
+    int total = 0;
+    int nextDY = y > p[0].y ? 1 : -1;
+    x[total] = p[0].x;
+    if (order == 2) {   /* edge-segments.cpp:289-341 */
+        if (p[0].y == y) {
+            if (p[0].y < p[1].y || (p[0].y == p[1].y && p[0].y < p[2].y))
+                dy[total++] = 1;
+            else
+                nextDY = 1;
+        }
+        {
+            v2 ab = vsub(p[1], p[0]);
+            v2 br = vsub(vsub(p[2], p[1]), ab);
+            double t[2];
+            int solutions = oracle_solve_quadratic(t, br.y, 2*ab.y, p[0].y-y);
+            double tmp;
+            if (solutions >= 2 && t[0] > t[1])
+                tmp = t[0], t[0] = t[1], t[1] = tmp;
+            for (int i = 0; i < solutions && total < 2; ++i) {
+                if (t[i] >= 0 && t[i] <= 1) {
+                    x[total] = p[0].x+2*t[i]*ab.x+t[i]*t[i]*br.x;
+                    if (nextDY*(ab.y+t[i]*br.y) >= 0) {
+                        dy[total++] = nextDY;
+                        nextDY = -nextDY;
+                    }
+                }
+            }
+        }
+        if (p[2].y == y) {
+            if (nextDY > 0 && total > 0) {
+                --total;
+                nextDY = -1;
+            }
+            if ((p[2].y < p[1].y || (p[2].y == p[1].y && p[2].y < p[0].y)) && total < 2) {
+                x[total] = p[2].x;
+                if (nextDY < 0) {
+                    dy[total++] = -1;
+                    nextDY = 1;
+                }
+            }
+        }
+        if (nextDY != (y >= p[2].y ? 1 : -1)) {
+            if (total > 0)
+                --total;
+            else {
+                if (fabs(p[2].y-y) < fabs(p[0].y-y))
+                    x[total] = p[2].x;
+                dy[total++] = nextDY;
+            }
+        }
+        return total;
+    }
+    /* cubic, edge-segments.cpp:343-403 */
+    if (p[0].y == y) {
+        if (p[0].y < p[1].y || (p[0].y == p[1].y && (p[0].y < p[2].y || (p[0].y == p[2].y && p[0].y < p[3].y))))
+            dy[total++] = 1;
+        else
+            nextDY = 1;
+    }
+    {
+        v2 ab = vsub(p[1], p[0]);
+        v2 br = vsub(vsub(p[2], p[1]), ab);
+        v2 as = vsub(vsub(vsub(p[3], p[2]), vsub(p[2], p[1])), br);
+        double t[3];
+        int solutions = oracle_solve_cubic(t, as.y, 3*br.y, 3*ab.y, p[0].y-y);
+        double tmp;
+        if (solutions >= 2) {
+            if (t[0] > t[1])
+                tmp = t[0], t[0] = t[1], t[1] = tmp;
+            if (solutions >= 3 && t[1] > t[2]) {
+                tmp = t[1], t[1] = t[2], t[2] = tmp;
+                if (t[0] > t[1])
+                    tmp = t[0], t[0] = t[1], t[1] = tmp;
+            }
+        }
+        for (int i = 0; i < solutions && total < 3; ++i) {
+            if (t[i] >= 0 && t[i] <= 1) {
+                x[total] = p[0].x+3*t[i]*ab.x+3*t[i]*t[i]*br.x+t[i]*t[i]*t[i]*as.x;
+                if (nextDY*(ab.y+2*t[i]*br.y+t[i]*t[i]*as.y) >= 0) {
+                    dy[total++] = nextDY;
+                    nextDY = -nextDY;
+                }
+            }
+        }
+    }
+    if (p[3].y == y) {
+        if (nextDY > 0 && total > 0) {
+            --total;
+            nextDY = -1;
+        }
+        if ((p[3].y < p[2].y || (p[3].y == p[2].y && (p[3].y < p[1].y || (p[3].y == p[1].y && p[3].y < p[0].y)))) && total < 3) {
+            x[total] = p[3].x;
+            if (nextDY < 0) {
+                dy[total++] = -1;
+                nextDY = 1;
+            }
+        }
+    }
+    if (nextDY != (y >= p[3].y ? 1 : -1)) {
+        if (total > 0)
+            --total;
+        else {
+            if (fabs(p[3].y-y) < fabs(p[0].y-y))
+                x[total] = p[3].x;
+            dy[total++] = nextDY;
+        }
+    }
+    return total;
+}
+
+/* interpretFillRule, Scanline.cpp:12-24: 0 NONZERO, 1 ODD, 2 POSITIVE, 3 NEGATIVE */
+static int fill_rule(int intersections, int rule) {
+    switch (rule) {
+        case 0: return intersections != 0;
+        case 1: return intersections&1;
+        case 2: return intersections > 0;
+        case 3: return intersections < 0;
+    }
+    return 0;
+}
+
+/* Scanline::filled(x) over Shape::scanline(y): the sum of the crossing directions of all intersections at or left of x
+ * (Scanline.cpp:72-123 sorts and prefix-sums; the sum itself does not depend on the order) */
+static int shape_filled(const flat_shape *s, double x, double y, int rule) {
+    int sum = 0;
+    uint32_t nSeg = s->cbegin[s->nContours];
+    for (uint32_t e = 0; e < nSeg; ++e) {
+        double ix[3];
+        int dy[3];
+        int n = seg_scanline(s->orders[e], s->pts+4*(size_t) e, ix, dy, y);
+        for (int i = 0; i < n; ++i)
+            if (ix[i] <= x)
+                sum += dy[i];
+    }
+    return fill_rule(sum, rule);
+}
+
+/* rasterize (rasterization.cpp:9-17) */
+int oracle_rasterize(int nContours, const uint32_t *cbegin, const double *points, const uint8_t *orders, int shapeYDown,
+                     const double *xf, float *out, int w, int h, int outYDown, int fillRule) {
+    flat_shape fs = { nContours, cbegin, (const v2 *) points, orders, NULL };
+    int flip = outYDown != shapeYDown;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            out[(size_t) (flip ? h-1-y : y)*w+x] = (float) shape_filled(&fs, (x+.5)/xf[0]-xf[2], (y+.5)/xf[1]-xf[3], fillRule);
+    return 0;
+}
+
+/* distanceSignCorrection for N = 1 (rasterization.cpp:19-32) and N = 3, 4 (multiDistanceSignCorrection :34-96); in place.
+ * xf: scale.x, scale.y, translate.x, translate.y (only the projection is used). */
+int oracle_sign_correction(int N, int nContours, const uint32_t *cbegin, const double *points, const uint8_t *orders, const uint8_t *colors, int shapeYDown,
+                           const double *xf, float *sdf, int w, int h, int rowStride, int sdfYDown, float zeroValue, int fillRule) {
+    (void) colors;
+    if (!(N == 1 || N == 3 || N == 4))
+        return -1;
+    if (!(w && h))
+        return 0;
+    flat_shape fs = { nContours, cbegin, (const v2 *) points, orders, NULL };
+    int flip = sdfYDown != shapeYDown;
+    float *base = flip ? sdf+(ptrdiff_t) rowStride*(h-1) : sdf;
+    ptrdiff_t stride = flip ? -(ptrdiff_t) rowStride : rowStride;
+    float dbl = zeroValue+zeroValue;
+    char *match = (char *) calloc((size_t) w*h, 1);
+    if (!match)
+        return -1;
+    int ambiguous = 0;
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            double px = (x+.5)/xf[0]-xf[2], py = (y+.5)/xf[1]-xf[3];   /* unprojectX / unprojectY */
+            int fill = shape_filled(&fs, px, py, fillRule);
+            float *msd = base+stride*y+(ptrdiff_t) N*x;
+            if (N == 1) {
+                if ((msd[0] > zeroValue) != fill)
+                    msd[0] = dbl-msd[0];
+                continue;
+            }
+            float sd = fmedian(msd[0], msd[1], msd[2]);
+            if (sd == zeroValue)
+                ambiguous = 1;
+            else if ((sd > zeroValue) != fill) {
+                msd[0] = dbl-msd[0];
+                msd[1] = dbl-msd[1];
+                msd[2] = dbl-msd[2];
+                match[(size_t) y*w+x] = -1;
+            } else
+                match[(size_t) y*w+x] = 1;
+            if (N >= 4 && (msd[3] > zeroValue) != fill)
+                msd[3] = dbl-msd[3];
+        }
+    if (N > 1 && ambiguous)
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x)
+                if (!match[(size_t) y*w+x]) {
+                    int nm = 0;
+                    if (x > 0) nm += match[(size_t) y*w+x-1];
+                    if (x < w-1) nm += match[(size_t) y*w+x+1];
+                    if (y > 0) nm += match[(size_t) (y-1)*w+x];
+                    if (y < h-1) nm += match[(size_t) (y+1)*w+x];
+                    if (nm < 0) {
+                        float *msd = base+stride*y+(ptrdiff_t) N*x;
+                        msd[0] = dbl-msd[0];
+                        msd[1] = dbl-msd[1];
+                        msd[2] = dbl-msd[2];
+                    }
+                }
+    free(match);
+    return 0;
+}
+
 /* pixelFloatToByte, core/pixel-conversion.hpp:8-10 (clamp: arithmetics.hpp:34-37) */
 void oracle_pixel_float_to_byte(const float *in, uint8_t *out, size_t n) {
     for (size_t i = 0; i < n; ++i) {

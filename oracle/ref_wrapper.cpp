@@ -300,6 +300,30 @@ int ref_read_shape_description(const char *text, int capSeg, int capContours, ui
     return flattenShape(shape, capSeg, capContours, outCbegin, outPoints, outOrders, outColors);
 }
 
+/// distanceSignCorrection(sdf, shape, projection, sdfZeroValue, fillRule) (core/rasterization.h), N = 1, 3 or 4; in place.
+int ref_sign_correction(int N, int nContours, const uint32_t *cbegin, const double *points, const uint8_t *orders, const uint8_t *colors, int yDown,
+                        const double *xf, float *sdf, int w, int h, int rowStride, int sdfYDown, float zeroValue, int fillRule) {
+    Shape shape;
+    buildShape(shape, nContours, cbegin, points, orders, colors, yDown);
+    Projection projection(Vector2(xf[0], xf[1]), Vector2(xf[2], xf[3]));
+    YAxisOrientation yo = sdfYDown ? Y_DOWNWARD : Y_UPWARD;
+    switch (N) {
+        case 1: distanceSignCorrection(BitmapSection<float, 1>(sdf, w, h, rowStride, yo), shape, projection, zeroValue, (FillRule) fillRule); return 0;
+        case 3: distanceSignCorrection(BitmapSection<float, 3>(sdf, w, h, rowStride, yo), shape, projection, zeroValue, (FillRule) fillRule); return 0;
+        case 4: distanceSignCorrection(BitmapSection<float, 4>(sdf, w, h, rowStride, yo), shape, projection, zeroValue, (FillRule) fillRule); return 0;
+    }
+    return -1;
+}
+
+/// rasterize(output, shape, projection, fillRule): 1.0 / 0.0 coverage at texel centres.
+int ref_rasterize(int nContours, const uint32_t *cbegin, const double *points, const uint8_t *orders, int yDown,
+                  const double *xf, float *out, int w, int h, int outYDown, int fillRule) {
+    Shape shape;
+    buildShape(shape, nContours, cbegin, points, orders, NULL, yDown);
+    rasterize(BitmapSection<float, 1>(out, w, h, w, outYDown ? Y_DOWNWARD : Y_UPWARD), shape, Projection(Vector2(xf[0], xf[1]), Vector2(xf[2], xf[3])), (FillRule) fillRule);
+    return 0;
+}
+
 void ref_pixel_float_to_byte(const float *in, uint8_t *out, size_t n) {
     for (size_t i = 0; i < n; ++i)
         out[i] = pixelFloatToByte(in[i]);

@@ -93,4 +93,28 @@ int caller_error_correction(int nContours, const uint32_t *cbegin, const double 
     return 0;
 }
 
+// The command line's scanline flow (no geometry preprocessing: contours are NOT oriented, signs come from the fill):
+// distance pass with correction postponed, distanceSignCorrection, msdfErrorCorrection; plus rasterize and the legacy overloads.
+// out: float[h][w][4] mtsdf | float[h][w][3] msdf (legacy scale/translate overload, FILL_ODD) | float[h][w] sdf | float[h][w] raster
+int caller_scanline(int nContours, const uint32_t *cbegin, const double *pts, const uint8_t *orders, int w, int h, float *out) {
+    Shape shape;
+    buildShape(shape, nContours, cbegin, pts, orders, 0);
+    // reverse every other contour: a shape as an un-preprocessed font outline may deliver it
+    for (size_t i = 1; i < shape.contours.size(); i += 2)
+        shape.contours[i].reverse();
+    edgeColoringSimple(shape, 3.0);
+    SDFTransformation t = autoframe(shape, w, h, 4.0);
+    MSDFGeneratorConfig off(true, ErrorCorrectionConfig(ErrorCorrectionConfig::DISABLED));
+    float *mtsdf = out, *msdf = out+size_t(w)*h*4, *sdf = msdf+size_t(w)*h*3, *raster = sdf+size_t(w)*h;
+    generateMTSDF(BitmapSection<float, 4>(mtsdf, w, h), shape, t, off);
+    distanceSignCorrection(BitmapSection<float, 4>(mtsdf, w, h), shape, t);
+    msdfErrorCorrection(BitmapSection<float, 4>(mtsdf, w, h), shape, t);
+    generateMSDF(BitmapSection<float, 3>(msdf, w, h), shape, t, off);
+    distanceSignCorrection(BitmapSection<float, 3>(msdf, w, h), shape, t.projectVector(Vector2(1)), -t.unproject(Point2(0)), FILL_ODD);
+    generateSDF(BitmapSection<float, 1>(sdf, w, h, w, Y_DOWNWARD), shape, t);
+    distanceSignCorrection(BitmapSection<float, 1>(sdf, w, h, w, Y_DOWNWARD), shape, t, .5f, FILL_POSITIVE);
+    rasterize(BitmapSection<float, 1>(raster, w, h), shape, t, FILL_NONZERO);
+    return 0;
+}
+
 }

@@ -23,19 +23,21 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_default_config():
     lib = _lib.load()
-    assert lib.b200msdf_version() == 100
+    assert lib.b200msdf_version() == 101
     cfg = _lib.Config()
     lib.b200msdf_default_config(C.byref(cfg))
     # MSDFGeneratorConfig() defaults, /root/reference/core/generator-config.h:46,52,62
     assert (cfg.overlap_support, cfg.ec_mode, cfg.ec_distance_check_mode) == (1, 2, 1)
     assert cfg.min_deviation_ratio == cfg.min_improve_ratio == 1.11111111111111111
+    # the scanline pass is off by default; distanceSignCorrection's defaults (core/rasterization.h:14)
+    assert (cfg.scanline_pass, cfg.fill_rule, cfg.sdf_zero_value) == (0, 0, 0.5)
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Transform) == 48
     assert C.sizeof(_lib.Bitmap) == 24
     assert C.sizeof(_lib.Shapes) == 64
-    assert C.sizeof(_lib.Config) == 40
+    assert C.sizeof(_lib.Config) == 56
 
 
 def test_no_cpu_fallback_without_device():

@@ -58,6 +58,9 @@ def _run(lib, g, w=24, h=20):
     st = np.zeros((h, w), np.uint8)
     assert lib.caller_error_correction(*_args(g), C.c_int(w), C.c_int(h), c.ctypes.data_as(C.POINTER(C.c_float)), st.ctypes.data_as(C.POINTER(C.c_uint8))) == 0
     res["ec"], res["stencil"] = c, st
+    d = np.full(h * w * 9, np.nan, np.float32)
+    assert lib.caller_scanline(*_args(g), C.c_int(w), C.c_int(h), d.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    res["scanline"] = d
     return res
 
 
@@ -84,7 +87,7 @@ def test_b200_build_matches_reference_build():
         g = synth_glyph(int(seed), cubic_fraction=0.2)
         mine = _run(b200, g)
         assert mine["edges"] == int(z[f"edges{i}"])
-        for key in ("msdf", "modes", "ec"):
+        for key in ("msdf", "modes", "ec", "scanline"):
             want = z[f"{key}{i}"]
             bits, max_abs, over = compare(mine[key], want)
             assert over == 0 and max_abs <= 1e-4, (key, seed, bits, max_abs)
