@@ -279,11 +279,11 @@ class Batch:
         cfg = (config or MSDFGeneratorConfig()).c()
         _lib.check(self.ctx.lib.b200msdf_batch_launch_stages(self.ctx.h, self.h, C.byref(cfg), stages))
 
-    @property
     def sign_correction(self, sdf_zero_value=0.5, fill_rule=FILL_NONZERO):
         """distanceSignCorrection on the batch's most recent device result, in place."""
         _lib.check(self.ctx.lib.b200msdf_batch_sign_correction(self.ctx.h, self.h, sdf_zero_value, fill_rule))
 
+    @property
     def output_floats(self):
         return int(self.ctx.lib.b200msdf_batch_output_floats(self.h))
 
