@@ -96,6 +96,9 @@ struct b200msdf_batch {
     float *current = nullptr;       // device pointer to the most recent result (raw field after k1, final output after a full launch)
     DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, field, out, stencil, candidates, candCount;
     DevBuf bytes, byteTargets;    // 8-bit output path
+    DevBuf blocks, blockWork;     // big shapes: 2-D block tiles of k1_big_blocks and its per-CTA list / cap workspace
+    int nBlocks = 0, maxBigSegs = 0, maxBigContours = 0;
+    std::vector<TileDesc> hBlocks;
     DevBuf counters, scratch;     // per batch, so that batches launched on different streams never share scheduling state
     std::vector<GlyphDesc> hGlyphs;
     std::vector<TileDesc> hTiles;
@@ -103,6 +106,7 @@ struct b200msdf_batch {
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
         bigGlyphs.release(); bigRecs.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); bytes.release(); byteTargets.release();
+        blocks.release(); blockWork.release();
     }
 };
 
@@ -171,6 +175,8 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     b->hGlyphs.resize((size_t) s->n_glyphs);
     b->hTiles.clear();
     b->hBig.clear();
+    b->hBlocks.clear();
+    b->maxBigSegs = b->maxBigContours = 0;
     size_t outFloats = 0, texels = 0, bigRecs = 0;
     int maxContours = 0;
     std::vector<TileDesc> bigTiles;
@@ -209,6 +215,18 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
             d.recBase = (int) bigRecs;
             bigRecs += nSeg;
             b->hBig.push_back(g);
+            if ((int) nSeg > b->maxBigSegs) b->maxBigSegs = (int) nSeg;
+            if ((int) (d.c1-d.c0) > b->maxBigContours) b->maxBigContours = (int) (d.c1-d.c0);
+            // the distance kernel walks big shapes in BLOCK_W x BLOCK_H blocks (tile-level culling)
+            if (px) {
+                unsigned nb = (unsigned) ((d.w+BLOCK_W-1)/BLOCK_W)*(unsigned) ((d.h+BLOCK_H-1)/BLOCK_H);
+                for (unsigned k = 0; k < nb; ++k) {
+                    TileDesc td;
+                    td.glyph = (unsigned) g;
+                    td.pix0 = k;
+                    b->hBlocks.push_back(td);
+                }
+            }
         } else
             d.recBase = -1;
         for (size_t p0 = 0; p0 < px; p0 += TILE_PIXELS) {
@@ -226,6 +244,7 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     b->nTiles = (int) b->hTiles.size();
     b->nBig = (int) b->hBig.size();
     b->nBigRecs = bigRecs;
+    b->nBlocks = (int) b->hBlocks.size();
 
     cudaStream_t st = ctx->stream;
     size_t nSeg = (size_t) s->n_segments, nCon = (size_t) s->n_contours;
@@ -248,6 +267,9 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
         if ((rc = b->bigGlyphs.reserve(sizeof(int)*b->hBig.size()))) return rc;
         if ((rc = b->bigRecs.reserve(sizeof(SegRec)*bigRecs))) return rc;
         CUDA_TRY(cudaMemcpyAsync(b->bigGlyphs.p, b->hBig.data(), sizeof(int)*b->hBig.size(), cudaMemcpyHostToDevice, st));
+        if ((rc = b->blocks.reserve(sizeof(TileDesc)*(b->hBlocks.size()+1)))) return rc;
+        if (!b->hBlocks.empty())
+            CUDA_TRY(cudaMemcpyAsync(b->blocks.p, b->hBlocks.data(), sizeof(TileDesc)*b->hBlocks.size(), cudaMemcpyHostToDevice, st));
     }
     if (nSeg) {
         CUDA_TRY(cudaMemcpyAsync(b->points.p, s->points, nSeg*64, cudaMemcpyHostToDevice, st));
@@ -310,8 +332,30 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
     int rc;
     P.tileBegin = 0; P.tileEnd = P.nSmallTiles; P.counterIndex = 0;
     if ((rc = launch_tiles(ctx, k1_distance_field<MODE, OVERLAP, false>, P, scratch))) return rc;
-    P.tileBegin = P.nSmallTiles; P.tileEnd = P.nTiles; P.counterIndex = 3;
-    if ((rc = launch_tiles(ctx, k1_distance_field<MODE, OVERLAP, true>, P, scratch))) return rc;
+    // big shapes: 2-D blocks with per-block record lists; each resident CTA owns a slice of the list / cap workspace
+    b200msdf_batch *b = ctx->cur;
+    if (b->nBlocks > 0) {
+        int grid = 1;
+        if ((rc = grid_for(ctx, k1_big_blocks<MODE, OVERLAP>, b->nBlocks, 0, CTA_THREADS, &grid))) return rc;
+        P.blocks = b->blocks.as<TileDesc>();
+        P.nBlocks = b->nBlocks;
+        P.listStride = ((size_t) b->maxBigSegs+3)&~size_t(3);
+        P.capStride = (size_t) (b->maxBigContours > 0 ? b->maxBigContours : 1)*ModeTraits<MODE>::NCH;
+        size_t capBytes = (size_t) grid*P.capStride*sizeof(unsigned long long);
+        if ((rc = b->blockWork.reserve(capBytes+(size_t) grid*P.listStride*sizeof(int)))) return rc;
+        P.blockCaps = b->blockWork.as<unsigned long long>();
+        P.blockList = reinterpret_cast<int *>(static_cast<char *>(b->blockWork.p)+capBytes);
+        P.scratchStride = (size_t) grid*CTA_THREADS;
+        if (scratch > 0) {
+            if ((rc = b->scratch.reserve(P.scratchStride*(size_t) scratch*sizeof(double)))) return rc;
+            P.scratch = b->scratch.as<double>();
+        } else
+            P.scratch = nullptr;
+        P.counterIndex = 3;
+        k1_big_blocks<MODE, OVERLAP><<<grid, CTA_THREADS, 0, ctx->stream>>>(P);
+        CUDA_TRY(cudaGetLastError());
+        ++ctx->launches;
+    }
     P.tileBegin = 0; P.tileEnd = P.nTiles; P.counterIndex = 0;
     return 0;
 }

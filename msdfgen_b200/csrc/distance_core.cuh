@@ -89,7 +89,7 @@ struct __align__(16) SegRec {
     int winding;           // Contour::winding() of the owning contour
     int cornerL, cornerB;  // texel l,b of protectCorners if this edge starts a colour corner, else INT_MIN/2
     int storageIndex;      // index of the segment in the caller's arrays
-    int pad;
+    int contour;           // index of the owning contour within the glyph (empty contours counted)
 };
 
 // Per-glyph geometry, built on the host when a batch is uploaded.
@@ -234,7 +234,7 @@ __device__ inline void prepare_record(const RawShapes &rs, const GlyphDesc &g, u
     int flags = (k == e-b-1) ? SEG_LAST_IN_CONTOUR : 0;
     out.winding = rs.windings[c];
     out.storageIndex = int(cur);
-    out.pad = 0;
+    out.contour = int(c-g.c0);
     #pragma unroll
     for (int i = 0; i < 14; ++i)
         out.e[i] = 0;
@@ -791,13 +791,40 @@ __device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, in
 // cap[] for the records [j0, j1]: per channel, the distance from p to the nearest START POINT of an edge of that channel
 // (an upper bound of the channel's minimum true distance; the tiny inflation absorbs rounding differences between this
 // expression and the segment kernels').
-template <int MODE>
-__device__ __forceinline__ void distance_caps(const SegRec *recs, int j0, int j1, d2 p, double *cap) {
+//
+// Record iteration: the walk below visits records i0..i1 of an ordered sequence.  SeqIter: the sequence is the glyph's
+// whole record array.  ListIter: an ordered SUBSET of it (tile-level culling of big shapes, k1_big_blocks) — valid whenever
+// every dropped record provably has no effect on any texel the list is used for.
+struct SeqIter {
+    __device__ __forceinline__ int at(int i) const { return i; }
+    // last position of the contour that starts at position i0
+    __device__ __forceinline__ int group_last(const SegRec *recs, int i0, int n) const {
+        int i1 = i0;
+        while (i1 < n-1 && !(recs[i1].flags&SEG_LAST_IN_CONTOUR))
+            ++i1;
+        return i1;
+    }
+};
+struct ListIter {
+    const int *list;
+    __device__ __forceinline__ int at(int i) const { return list[i]; }
+    __device__ __forceinline__ int group_last(const SegRec *recs, int i0, int n) const {
+        const int contour = recs[list[i0]].contour;
+        int i1 = i0;
+        while (i1 < n-1 && recs[list[i1+1]].contour == contour)
+            ++i1;
+        return i1;
+    }
+};
+
+template <int MODE, typename IT>
+__device__ __forceinline__ void distance_caps(const SegRec *recs, IT it, int j0, int j1, d2 p, double *cap) {
     double capsq[ModeTraits<MODE>::NCH];
     #pragma unroll
     for (int k = 0; k < ModeTraits<MODE>::NCH; ++k)
         capsq[k] = DBL_MAX;
-    for (int j = j0; j <= j1; ++j) {
+    for (int i = j0; i <= j1; ++i) {
+        const int j = it.at(i);
         const int mask = (MODE == 1 || MODE == 2) ? 1 : recs[j].color;
         d2 v = p-recs[j].p0;
         double q = dot(v, v);
@@ -870,17 +897,19 @@ __device__ __forceinline__ void load_selector(ContourStore &st, int c, Sel<MODE>
 // ShapeDistanceFinder<Combiner<Selector>>::oneShotDistance at point p over the glyph's records [0, nRec).
 // recs is shared memory (small glyphs) or the global prepared buffer (big shapes); every thread of the CTA walks the same
 // record at the same time, so loads broadcast.  out gets NOUT raw (unmapped) fp64 distances.
-template <int MODE, bool OVERLAP>
-__device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, d2 p, ContourStore store, double *out) {
+template <int MODE, bool OVERLAP, typename IT>
+__device__ __forceinline__ void shape_distance_over(const SegRec *recs, int nRec, IT it, d2 p, ContourStore store, double *out) {
     const int NOUT = ModeTraits<MODE>::NOUT;
     typedef StoreLayout<MODE> L;
     if (!OVERLAP) {
         Sel<MODE> sel;
         sel_init(sel);
         double cap[ModeTraits<MODE>::NCH];
-        distance_caps<MODE>(recs, 0, nRec-1, p, cap);
-        for (int j = 0; j < nRec; ++j)
+        distance_caps<MODE>(recs, it, 0, nRec-1, p, cap);
+        for (int i = 0; i < nRec; ++i) {
+            const int j = it.at(i);
             sel_add_edge<MODE>(sel, recs[j], j, p, cap);
+        }
         sel_distance<MODE>(sel, recs, p, out);
     } else {
         // ---- walk the edges with ONE live selector; park each finished contour
@@ -890,21 +919,21 @@ __device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, d2 
             sel_init(cur);
             int j0 = 0;
             while (j0 < nRec) {
-                // the contour's records are [j0, j1]; its closing record carries SEG_LAST_IN_CONTOUR
-                int j1 = j0;
-                while (j1 < nRec-1 && !(recs[j1].flags&SEG_LAST_IN_CONTOUR))
-                    ++j1;
+                // the contour's records are at positions [j0, j1] (SeqIter: its closing record carries SEG_LAST_IN_CONTOUR)
+                const int j1 = it.group_last(recs, j0, nRec);
                 double cap[ModeTraits<MODE>::NCH];
-                distance_caps<MODE>(recs, j0, j1, p, cap);
-                for (int j = j0; j <= j1; ++j)
+                distance_caps<MODE>(recs, it, j0, j1, p, cap);
+                for (int i = j0; i <= j1; ++i) {
+                    const int j = it.at(i);
                     sel_add_edge<MODE>(cur, recs[j], j, p, cap);
+                }
                 double cd[NOUT];
                 sel_distance<MODE>(cur, recs, p, cd);
                 store_selector<MODE>(store, nc, cur);
                 #pragma unroll
                 for (int k = 0; k < NOUT; ++k)
                     store.at(nc, L::DIST+k) = cd[k];
-                store.at(nc, L::WINDING) = double(recs[j1].winding);
+                store.at(nc, L::WINDING) = double(recs[it.at(j1)].winding);
                 sel_init(cur);
                 ++nc;
                 j0 = j1+1;
@@ -978,6 +1007,11 @@ __device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, d2 
         #pragma unroll
         for (int k = 0; k < NOUT; ++k) out[k] = dist[k];
     }
+}
+
+template <int MODE, bool OVERLAP>
+__device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, d2 p, ContourStore store, double *out) {
+    shape_distance_over<MODE, OVERLAP>(recs, nRec, SeqIter(), p, store, out);
 }
 
 }  // namespace b200

@@ -39,6 +39,12 @@ struct KernelParams {
     float *field;                 // k1 output (k2 input)
     float *out;                   // k2 output
     uint8_t *stencil;             // k2: per-texel flags (1 = ERROR, 2 = PROTECTED), rows in Y-up order like the reference's buffer
+    // big shapes (> SMEM_RECORDS segments): 2-D blocks of BLOCK_W x BLOCK_H texels with per-block record lists
+    const TileDesc *blocks;       // {glyph, block index (row-major over the glyph's block grid)}
+    int nBlocks;
+    int *blockList;               // per-CTA workspace: listStride record indices
+    unsigned long long *blockCaps;// per-CTA workspace: capStride squared distances (as ordered bit patterns)
+    size_t listStride, capStride;
     double *scratch;              // per-thread contour-distance slices for many-contour shapes
     size_t scratchStride;         // = gridDim.x * CTA_THREADS
     // error correction config
@@ -211,6 +217,161 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
             __syncthreads();
             unsigned nPix = tileEnd-passBase < CTA_THREADS ? tileEnd-passBase : CTA_THREADS;
             store_tile(P.field+s_g.outOffset+size_t(passBase)*NOUT, s_out, int(nPix)*NOUT);
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Big shapes: tile-level culling.
+//
+// A shape with thousands of segments (BASELINE configs[3]: 10 000) makes every texel walk every record, although the exact
+// per-texel culling of sel_add_edge then skips the math of nearly all of them.  Here a tile is a BLOCK_W x BLOCK_H block of
+// texels; before its texels are evaluated the CTA builds the ordered list of records that can matter ANYWHERE in the block,
+// and the texels walk only that list (ListIter).  A record is dropped only if, for every texel p of the block,
+// sel_add_edge would take its `culled` path AND reject both perpendicular candidates, i.e. it provably has no effect:
+//
+//   c = block centre, hd = half diagonal of the block's texel centres (so |p - c| <= hd), and per contour (OVERLAP) or per
+//   shape (simple combiner) and channel k:  capT[k] = min over records with channel k of |c - p0| + hd.
+//   For every texel, cap[k](p) <= capT[k]: the record attaining the minimum is itself listed (its circle contains p0), and
+//   |p - p0| <= |c - p0| + hd.  With needT = max over the record's channels of capT[k] >= need(p):
+//     * |c - bc| - hd - br > needT   =>  |p - bc| > br + need(p)                     => culled at p;
+//     * | cross(c - p0, aDir) | - hd > needT  =>  |pdA(p)| > need(p)                 => candidate A rejected (aDir is a unit
+//       vector or zero, so pdA is 1-Lipschitz); same for B with pEnd, bDir.
+//   All comparisons carry a relative slack of 1e-8 (rounding is ~1e-16) and NaNs compare as "keep".
+// The list preserves the evaluation order, so ties resolve exactly as in the full walk.  Results are bit-identical.
+#define BLOCK_W 32
+#define BLOCK_H 32
+
+template <int MODE, bool OVERLAP>
+__global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) {
+    const int NOUT = ModeTraits<MODE>::NOUT;
+    const int NCH = ModeTraits<MODE>::NCH;
+    const int ROWS = CTA_THREADS/BLOCK_W;           // texel rows per pass
+    __shared__ __align__(16) float s_out[CTA_THREADS*NOUT];
+    __shared__ GlyphDesc s_g;
+    __shared__ int s_tile;
+    __shared__ int s_warpKeep[CTA_THREADS/32];
+    int *list = P.blockList+size_t(blockIdx.x)*P.listStride;
+    unsigned long long *caps = P.blockCaps+size_t(blockIdx.x)*P.capStride;
+    double localStore[OVERLAP ? B200_LOCAL_CONTOURS*StoreLayout<MODE>::PER_CONTOUR : 1];
+    int stagedGlyph = -1;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_tile = atomicAdd(&P.counters[P.counterIndex], 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= P.nBlocks)
+            break;
+        const TileDesc td = P.blocks[tile];
+        if ((int) td.glyph != stagedGlyph) {
+            if (threadIdx.x == 0)
+                s_g = P.glyphs[td.glyph];
+            stagedGlyph = (int) td.glyph;
+            __syncthreads();
+        }
+        const SegRec *recs = P.bigRecs+s_g.recBase;
+        const int nRec = int(s_g.s1-s_g.s0);
+        const int w = s_g.w, h = s_g.h;
+        const int blocksX = (w+BLOCK_W-1)/BLOCK_W;
+        const int bx0 = int(td.pix0%unsigned(blocksX))*BLOCK_W, by0 = int(td.pix0/unsigned(blocksX))*BLOCK_H;
+        // block centre and half diagonal in shape units (texel centres span +-(BLOCK-1)/2 pixels around the centre)
+        const double cpx = s_g.x0+bx0+.5*BLOCK_W;
+        const double cpy = s_g.y0+(s_g.flip ? h-by0-.5*BLOCK_H : by0+.5*BLOCK_H);
+        const d2 c = mk(cpx/s_g.sx-s_g.tx, cpy/s_g.sy-s_g.ty);
+        const double hx = .5*(BLOCK_W-1)/fabs(s_g.sx), hy = .5*(BLOCK_H-1)/fabs(s_g.sy);
+        const double hd = sqrt(hx*hx+hy*hy)*(1+1e-9)+1e-12*(fabs(c.x)+fabs(c.y)+fabs(s_g.tx)+fabs(s_g.ty));
+
+        // ---- phase 1: capT per (contour | shape, channel)
+        const int nGroups = OVERLAP ? int(s_g.c1-s_g.c0) : 1;
+        for (int i = threadIdx.x; i < nGroups*NCH; i += CTA_THREADS)
+            caps[i] = ~0ull;
+        __syncthreads();
+        for (int j = threadIdx.x; j < nRec; j += CTA_THREADS) {
+            const int mask = (MODE == 1 || MODE == 2) ? 1 : recs[j].color;
+            const int grp = OVERLAP ? recs[j].contour : 0;
+            d2 v = c-recs[j].p0;
+            unsigned long long q = (unsigned long long) __double_as_longlong(dot(v, v));      // >= 0: bit patterns order like values
+            #pragma unroll
+            for (int k = 0; k < NCH; ++k)
+                if (mask&(1<<k))
+                    atomicMin(&caps[grp*NCH+k], q);
+        }
+        __syncthreads();
+        // ---- phase 2: ordered list of the records that can matter in this block
+        int nList = 0;
+        for (int base = 0; base < nRec; base += CTA_THREADS) {
+            const int j = base+int(threadIdx.x);
+            bool keep = false;
+            if (j < nRec) {
+                const int mask = (MODE == 1 || MODE == 2) ? 1 : recs[j].color;
+                const int grp = OVERLAP ? recs[j].contour : 0;
+                double needT = 0;
+                #pragma unroll
+                for (int k = 0; k < NCH; ++k)
+                    if (mask&(1<<k))
+                        needT = dmax(needT, sqrt(__longlong_as_double((long long) caps[grp*NCH+k])));
+                needT = (needT+hd)*(1+1e-8);
+                d2 v = c-recs[j].bc;
+                const double reach = needT+recs[j].br+hd;
+                keep = !(dot(v, v) > reach*reach*(1+1e-8));
+                if (MODE != 1 && !keep) {
+                    const double lim = needT+hd;
+                    keep = !(fabs(cross(c-recs[j].p0, recs[j].aDir)) > lim) || !(fabs(cross(c-recs[j].pEnd, recs[j].bDir)) > lim);
+                }
+            }
+            const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+            const unsigned lane = threadIdx.x&31, warp = threadIdx.x>>5;
+            if (lane == 0)
+                s_warpKeep[warp] = __popc(ballot);
+            __syncthreads();
+            int before = 0, total = 0;
+            #pragma unroll
+            for (int k = 0; k < CTA_THREADS/32; ++k) {
+                const int n = s_warpKeep[k];
+                if (k < int(warp)) before += n;
+                total += n;
+            }
+            if (keep)
+                list[nList+before+__popc(ballot&((1u<<lane)-1u))] = j;
+            nList += total;
+            __syncthreads();
+        }
+        // (the list stores above are ordered before the reads below by the last barrier of the loop)
+        ListIter it;
+        it.list = list;
+        ContourStore store;
+        store.perContour = StoreLayout<MODE>::PER_CONTOUR;
+        if (OVERLAP && s_g.nonEmptyContours > B200_LOCAL_CONTOURS) {
+            store.base = P.scratch+(size_t(blockIdx.x)*CTA_THREADS+threadIdx.x);
+            store.stride = P.scratchStride;
+        } else {
+            store.base = localStore;
+            store.stride = 1;
+        }
+        // ---- phase 3: the texels; a warp takes an 8x4 sub-block per pass, like k1_distance_field
+        for (int pass = 0; pass < BLOCK_H/ROWS; ++pass) {
+            const unsigned warp = threadIdx.x>>5, lane = threadIdx.x&31;
+            const int xl = int(warp%(BLOCK_W/8))*8+int(lane&7);
+            const int yl = int(warp/(BLOCK_W/8))*4+int(lane>>3);         // row inside the pass: 0 .. ROWS-1
+            const int x = bx0+xl, yOut = by0+pass*ROWS+yl;
+            if (x < w && yOut < h) {
+                const int y = s_g.flip ? h-1-yOut : yOut;
+                d2 p = mk((s_g.x0+x+.5)/s_g.sx-s_g.tx, (s_g.y0+y+.5)/s_g.sy-s_g.ty);
+                double dist[NOUT];
+                shape_distance_over<MODE, OVERLAP>(recs, nList, it, p, store, dist);
+                #pragma unroll
+                for (int k = 0; k < NOUT; ++k)
+                    s_out[(yl*BLOCK_W+xl)*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < ROWS*BLOCK_W*NOUT; i += CTA_THREADS) {
+                const int row = i/(BLOCK_W*NOUT), col = i%(BLOCK_W*NOUT);
+                const int yo = by0+pass*ROWS+row;
+                if (yo < h && bx0+col/NOUT < w)
+                    P.field[s_g.outOffset+(size_t(yo)*w+bx0)*NOUT+col] = s_out[i];
+            }
             __syncthreads();
         }
     }

@@ -143,6 +143,40 @@ def test_big_shape_many_contours(ctx, port):
             assert_parity(out, want, f"big {mode_name} overlap={ov}")
 
 
+def test_big_shape_block_lists_vs_port(ctx, port):
+    """Tile-level culling of big shapes (k1_big_blocks: 32x32 blocks with per-block record lists): every mode and combiner at
+    sizes that are not multiples of the block, flipped output, a batch mixing big and small shapes, anisotropic projection."""
+    big = prep.prepare(synth_big_shape(n_contours=30, segs_per_contour=40, seed=11))
+    assert big.n_segments == 1200
+    cb, pts, od, cl, _ = big.glyph(0)
+    w, h = 100, 70
+    xf = glyph_transform(w, h, px_range=5.0)
+    for mode_name in ("sdf", "psdf", "msdf", "mtsdf"):
+        for ov in (True, False):
+            cfg = api.MSDFGeneratorConfig(overlapSupport=ov)
+            for oyd in (False, True):
+                out = np.full((h, w, api.CHANNELS[MODE[mode_name]]), np.nan, np.float32)
+                ctx.generate(MODE[mode_name], out, big, xf, cfg, out_ydown=oyd)
+                want = port.generate(mode_name, cb, pts, od, cl, xf, w, h, _ocfg(cfg), out_ydown=oyd)
+                bits = assert_parity(out, want, f"blocks {mode_name} overlap={ov} ydown={oyd}")
+                assert bits == 0, f"blocks {mode_name} overlap={ov}: {bits} differing floats"
+    # zoomed in: the image shows a small part of the shape (most records are far from every block)
+    zoom = np.array([400.0, 300.0, -0.35, -0.4, -0.01, 0.01])
+    out = np.empty((64, 96, 3), np.float32)
+    ctx.generate(api.MSDF, out, big, zoom)
+    assert assert_parity(out, port.generate("msdf", cb, pts, od, cl, zoom, 96, 64, Config()), "blocks zoom") == 0
+    # big and small shapes in one batch
+    small = prep.prepare(synth_atlas(3, seed=5))
+    mixed = FlatShapes.concat([small, big, small])
+    outs = [np.empty((20, 20, 4), np.float32) for _ in range(3)] + [np.empty((45, 33, 4), np.float32)] + [np.empty((20, 20, 4), np.float32) for _ in range(3)]
+    xfs = np.stack([glyph_transform(20)] * 3 + [glyph_transform(33, 45, px_range=3.0)] + [glyph_transform(20)] * 3)
+    ctx.generate_batch(api.MTSDF, outs, mixed, xfs)
+    for g in range(7):
+        c2, p2, o2, l2, _ = mixed.glyph(g)
+        hh, ww = outs[g].shape[:2]
+        assert assert_parity(outs[g], port.generate("mtsdf", c2, p2, o2, l2, xfs[g], ww, hh, Config()), f"mixed batch glyph {g}") == 0
+
+
 def test_resident_batch_equals_host_api(ctx):
     atlas = prep.prepare(synth_atlas(64, seed=8800))
     xf = glyph_transform(32)
