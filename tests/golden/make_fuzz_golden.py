@@ -18,7 +18,7 @@ from util import fuzz_shape, fuzz_configs, digest  # noqa: E402
 
 ref = Oracle("reference")
 out = {}
-for seed in range(96):
+for seed in range(108):
     fam, cb, pts, od, cl, xf, w, h = fuzz_shape(seed)
     for key, mode, cfg in fuzz_configs(seed):
         f = ref.generate(mode, cb, pts, od, cl, xf, w, h, cfg)
