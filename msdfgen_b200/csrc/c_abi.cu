@@ -342,7 +342,9 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
         P.listStride = ((size_t) b->maxBigSegs+3)&~size_t(3);
         P.capStride = (size_t) (b->maxBigContours > 0 ? b->maxBigContours : 1)*ModeTraits<MODE>::NCH;
         size_t capBytes = (size_t) grid*P.capStride*sizeof(unsigned long long);
-        if ((rc = b->blockWork.reserve(capBytes+(size_t) grid*P.listStride*sizeof(int)))) return rc;
+        // per CTA: listStride record indices followed by up to maxBigContours group ends
+        P.listPerCta = P.listStride+(((size_t) b->maxBigContours+4)&~size_t(3));
+        if ((rc = b->blockWork.reserve(capBytes+(size_t) grid*P.listPerCta*sizeof(int)))) return rc;
         P.blockCaps = b->blockWork.as<unsigned long long>();
         P.blockList = reinterpret_cast<int *>(static_cast<char *>(b->blockWork.p)+capBytes);
         P.scratchStride = (size_t) grid*CTA_THREADS;

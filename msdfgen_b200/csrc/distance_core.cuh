@@ -807,14 +807,10 @@ struct SeqIter {
 };
 struct ListIter {
     const int *list;
+    const int *groupEnd;    // groupEnd[g] = position after the last listed record of the g-th listed contour (ascending)
+    mutable int group;      // next entry of groupEnd (the walk visits the groups in order, once)
     __device__ __forceinline__ int at(int i) const { return list[i]; }
-    __device__ __forceinline__ int group_last(const SegRec *recs, int i0, int n) const {
-        const int contour = recs[list[i0]].contour;
-        int i1 = i0;
-        while (i1 < n-1 && recs[list[i1+1]].contour == contour)
-            ++i1;
-        return i1;
-    }
+    __device__ __forceinline__ int group_last(const SegRec *, int, int) const { return groupEnd[group++]-1; }
 };
 
 template <int MODE, typename IT>

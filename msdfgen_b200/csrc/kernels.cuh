@@ -42,9 +42,9 @@ struct KernelParams {
     // big shapes (> SMEM_RECORDS segments): 2-D blocks of BLOCK_W x BLOCK_H texels with per-block record lists
     const TileDesc *blocks;       // {glyph, block index (row-major over the glyph's block grid)}
     int nBlocks;
-    int *blockList;               // per-CTA workspace: listStride record indices
+    int *blockList;               // per-CTA workspace: listStride record indices, then the group ends
     unsigned long long *blockCaps;// per-CTA workspace: capStride squared distances (as ordered bit patterns)
-    size_t listStride, capStride;
+    size_t listStride, listPerCta, capStride;   // list capacity; ints per CTA (list + group ends); cap slots per CTA
     double *scratch;              // per-thread contour-distance slices for many-contour shapes
     size_t scratchStride;         // = gridDim.x * CTA_THREADS
     // error correction config
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
     __shared__ GlyphDesc s_g;
     __shared__ int s_tile;
     __shared__ int s_warpKeep[CTA_THREADS/32];
-    int *list = P.blockList+size_t(blockIdx.x)*P.listStride;
+    int *list = P.blockList+size_t(blockIdx.x)*P.listPerCta;
     unsigned long long *caps = P.blockCaps+size_t(blockIdx.x)*P.capStride;
     double localStore[OVERLAP ? B200_LOCAL_CONTOURS*StoreLayout<MODE>::PER_CONTOUR : 1];
     int stagedGlyph = -1;
@@ -339,8 +339,36 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
             __syncthreads();
         }
         // (the list stores above are ordered before the reads below by the last barrier of the loop)
+        // group ends: position i closes a contour's run when the next listed record belongs to another contour; the runs are
+        // numbered by counting the closing positions before them (ordered compaction again, 256 positions per round)
+        int *groupEnd = list+P.listStride;
+        if (OVERLAP) {
+            int nGroupsListed = 0;
+            for (int base = 0; base < nList; base += CTA_THREADS) {
+                const int i = base+int(threadIdx.x);
+                const bool closes = i < nList && (i == nList-1 || recs[list[i+1]].contour != recs[list[i]].contour);
+                const unsigned ballot = __ballot_sync(0xffffffffu, closes);
+                const unsigned lane = threadIdx.x&31, warp = threadIdx.x>>5;
+                if (lane == 0)
+                    s_warpKeep[warp] = __popc(ballot);
+                __syncthreads();
+                int before = 0, total = 0;
+                #pragma unroll
+                for (int k = 0; k < CTA_THREADS/32; ++k) {
+                    const int n = s_warpKeep[k];
+                    if (k < int(warp)) before += n;
+                    total += n;
+                }
+                if (closes)
+                    groupEnd[nGroupsListed+before+__popc(ballot&((1u<<lane)-1u))] = i+1;
+                nGroupsListed += total;
+                __syncthreads();
+            }
+        }
         ListIter it;
         it.list = list;
+        it.groupEnd = groupEnd;
+        it.group = 0;
         ContourStore store;
         store.perContour = StoreLayout<MODE>::PER_CONTOUR;
         if (OVERLAP && s_g.nonEmptyContours > B200_LOCAL_CONTOURS) {
@@ -360,6 +388,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
                 const int y = s_g.flip ? h-1-yOut : yOut;
                 d2 p = mk((s_g.x0+x+.5)/s_g.sx-s_g.tx, (s_g.y0+y+.5)/s_g.sy-s_g.ty);
                 double dist[NOUT];
+                it.group = 0;
                 shape_distance_over<MODE, OVERLAP>(recs, nList, it, p, store, dist);
                 #pragma unroll
                 for (int k = 0; k < NOUT; ++k)
