@@ -94,7 +94,7 @@ struct b200msdf_batch {
     float *outOverride = nullptr;   // final texels go here instead of `out` (device-accessible pinned host memory of the caller)
     bool ecRan = false;
     float *current = nullptr;       // device pointer to the most recent result (raw field after k1, final output after a full launch)
-    DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, field, out, stencil, candidates, candCount;
+    DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, bigCull, bigPerp, field, out, stencil, candidates, candCount;
     DevBuf bytes, byteTargets;    // 8-bit output path
     DevBuf blocks, blockWork;     // big shapes: 2-D block tiles of k1_big_blocks and its per-CTA list / cap workspace
     int nBlocks = 0, maxBigSegs = 0, maxBigContours = 0;
@@ -105,7 +105,7 @@ struct b200msdf_batch {
     std::vector<int> hBig;
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
-        bigGlyphs.release(); bigRecs.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); bytes.release(); byteTargets.release();
+        bigGlyphs.release(); bigRecs.release(); bigCull.release(); bigPerp.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); bytes.release(); byteTargets.release();
         blocks.release(); blockWork.release();
     }
 };
@@ -266,6 +266,8 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     if (b->nBig) {
         if ((rc = b->bigGlyphs.reserve(sizeof(int)*b->hBig.size()))) return rc;
         if ((rc = b->bigRecs.reserve(sizeof(SegRec)*bigRecs))) return rc;
+        if ((rc = b->bigCull.reserve(sizeof(CullRec)*bigRecs))) return rc;
+        if ((rc = b->bigPerp.reserve(sizeof(PerpRec)*bigRecs))) return rc;
         CUDA_TRY(cudaMemcpyAsync(b->bigGlyphs.p, b->hBig.data(), sizeof(int)*b->hBig.size(), cudaMemcpyHostToDevice, st));
         if ((rc = b->blocks.reserve(sizeof(TileDesc)*(b->hBlocks.size()+1)))) return rc;
         if (!b->hBlocks.empty())
@@ -427,6 +429,8 @@ void fill_params(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
     P.counterIndex = 0;
     P.nContours = b->nContours;
     P.bigRecs = b->bigRecs.as<SegRec>();
+    P.bigCull = b->bigCull.as<CullRec>();
+    P.bigPerp = b->bigPerp.as<PerpRec>();
     P.counters = b->counters.as<int>();
     ctx->cur = b;
     P.ecMode = cfg->ec_mode;
@@ -444,7 +448,7 @@ int launch_prologue(b200msdf_ctx *ctx, b200msdf_batch *b, KernelParams &P) {
     ++ctx->launches;
     if (b->nBig) {
         dim3 grid(64, (unsigned) (b->nBig < 1024 ? b->nBig : 1024));
-        k0_prepare_big<<<grid, 128, 0, ctx->stream>>>(P.raw, P.glyphs, b->bigGlyphs.as<int>(), b->nBig, b->bigRecs.as<SegRec>());
+        k0_prepare_big<<<grid, 128, 0, ctx->stream>>>(P.raw, P.glyphs, b->bigGlyphs.as<int>(), b->nBig, b->bigRecs.as<SegRec>(), b->bigCull.as<CullRec>(), b->bigPerp.as<PerpRec>());
         CUDA_TRY(cudaGetLastError());
         ++ctx->launches;
     }

@@ -22,6 +22,10 @@ namespace b200 {
 
 struct TileDesc { unsigned glyph, pix0; };
 
+// Compact copies of the fields the tile-level culling of big shapes reads (48 B each instead of a 352 B SegRec)
+struct CullRec { d2 bc; double br; int color, contour; d2 p0; };
+struct PerpRec { d2 pEnd, aDir, bDir; };
+
 struct KernelParams {
     RawShapes raw;
     const GlyphDesc *glyphs;
@@ -32,6 +36,8 @@ struct KernelParams {
     int counterIndex;             // which counter this launch pulls tiles from
     int nContours;
     const SegRec *bigRecs;        // prepared records of big shapes
+    const CullRec *bigCull;       // same indexing as bigRecs
+    const PerpRec *bigPerp;
     int *counters;                // tile counters: [0],[3] k1 small/big, [1] k2, [2],[4] k3 small/big
     struct Candidate *candidates; // k2 -> k3: per-tile slots of exact-distance checks, candCap per tile
     int *candCount;               // per-tile number of pushes (may exceed candCap: overflow texels carry EC_FLAG_RECHECK)
@@ -67,12 +73,20 @@ __global__ void k0_windings(RawShapes raw, int nContours, int8_t *windings, int 
 }
 
 // items: (glyph index, evaluation position) pairs are implied by a prefix table: bigGlyphs[i] = glyph index, bigBase[i] = first record
-__global__ void k0_prepare_big(RawShapes raw, const GlyphDesc *glyphs, const int *bigGlyphs, int nBig, SegRec *recs) {
+__global__ void k0_prepare_big(RawShapes raw, const GlyphDesc *glyphs, const int *bigGlyphs, int nBig, SegRec *recs, CullRec *cull, PerpRec *perp) {
     for (int i = blockIdx.y; i < nBig; i += gridDim.y) {
         GlyphDesc g = glyphs[bigGlyphs[i]];
         unsigned n = g.s1-g.s0;
-        for (unsigned j = blockIdx.x*blockDim.x+threadIdx.x; j < n; j += gridDim.x*blockDim.x)
-            prepare_record(raw, g, j, recs[size_t(g.recBase)+j]);
+        for (unsigned j = blockIdx.x*blockDim.x+threadIdx.x; j < n; j += gridDim.x*blockDim.x) {
+            SegRec &r = recs[size_t(g.recBase)+j];
+            prepare_record(raw, g, j, r);
+            CullRec c;
+            c.bc = r.bc; c.br = r.br; c.color = r.color; c.contour = r.contour; c.p0 = r.p0;
+            cull[size_t(g.recBase)+j] = c;
+            PerpRec q;
+            q.pEnd = r.pEnd; q.aDir = r.aDir; q.bDir = r.bDir;
+            perp[size_t(g.recBase)+j] = q;
+        }
     }
 }
 
@@ -223,38 +237,59 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Big shapes: tile-level culling.
+// Big shapes: two-level tile culling.
 //
 // A shape with thousands of segments (BASELINE configs[3]: 10 000) makes every texel walk every record, although the exact
 // per-texel culling of sel_add_edge then skips the math of nearly all of them.  Here a tile is a BLOCK_W x BLOCK_H block of
-// texels; before its texels are evaluated the CTA builds the ordered list of records that can matter ANYWHERE in the block,
-// and the texels walk only that list (ListIter).  A record is dropped only if, for every texel p of the block,
-// sel_add_edge would take its `culled` path AND reject both perpendicular candidates, i.e. it provably has no effect:
+// texels.  Level 1: the CTA builds the ordered list of records that can matter ANYWHERE in the block.  Level 2: each warp
+// refines that list for the 8x4 sub-block it evaluates in the current pass (one lane tests one record, so the refinement
+// costs 1/32 of a walk).  The texels walk only the sub-list (ListIter).  A record is dropped for a region R (block or
+// sub-block) only if, for every texel p of R, sel_add_edge would take its `culled` path AND reject both perpendicular
+// candidates, i.e. it provably has no effect:
 //
-//   c = block centre, hd = half diagonal of the block's texel centres (so |p - c| <= hd), and per contour (OVERLAP) or per
-//   shape (simple combiner) and channel k:  capT[k] = min over records with channel k of |c - p0| + hd.
-//   For every texel, cap[k](p) <= capT[k]: the record attaining the minimum is itself listed (its circle contains p0), and
+//   c = centre of R, hd = half diagonal of R's texel centres (so |p - c| <= hd), and per contour (OVERLAP) or per shape
+//   (simple combiner) and channel k:  capT[k] = min over the candidate records with channel k of |c - p0| + hd.
+//   For every texel, cap[k](p) <= capT[k]: the record attaining the minimum is itself kept (its circle contains p0), and
 //   |p - p0| <= |c - p0| + hd.  With needT = max over the record's channels of capT[k] >= need(p):
 //     * |c - bc| - hd - br > needT   =>  |p - bc| > br + need(p)                     => culled at p;
 //     * | cross(c - p0, aDir) | - hd > needT  =>  |pdA(p)| > need(p)                 => candidate A rejected (aDir is a unit
 //       vector or zero, so pdA is 1-Lipschitz); same for B with pEnd, bDir.
 //   All comparisons carry a relative slack of 1e-8 (rounding is ~1e-16) and NaNs compare as "keep".
-// The list preserves the evaluation order, so ties resolve exactly as in the full walk.  Results are bit-identical.
+// The lists preserve the evaluation order, so ties resolve exactly as in the full walk.  Results are bit-identical.
 #define BLOCK_W 32
 #define BLOCK_H 32
+#define SUB_CAP 1024        // record indices per warp sub-list (shared memory); overflow -> the warp walks the block list
+#define SUB_GROUPS 256      // contour groups per warp sub-list
+
+template <int MODE>
+__device__ __forceinline__ bool region_keeps(const CullRec &cr, const PerpRec *perp, int j, d2 c, double hd, double needT) {
+    d2 v = c-cr.bc;
+    const double reach = needT+cr.br+hd;
+    bool keep = !(dot(v, v) > reach*reach*(1+1e-8));
+    if (MODE != 1 && !keep) {
+        const double lim = needT+hd;
+        const PerpRec q = perp[j];
+        keep = !(fabs(cross(c-cr.p0, q.aDir)) > lim) || !(fabs(cross(c-q.pEnd, q.bDir)) > lim);
+    }
+    return keep;
+}
 
 template <int MODE, bool OVERLAP>
 __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) {
     const int NOUT = ModeTraits<MODE>::NOUT;
     const int NCH = ModeTraits<MODE>::NCH;
     const int ROWS = CTA_THREADS/BLOCK_W;           // texel rows per pass
+    const int WARPS = CTA_THREADS/32;
     __shared__ __align__(16) float s_out[CTA_THREADS*NOUT];
     __shared__ GlyphDesc s_g;
     __shared__ int s_tile;
-    __shared__ int s_warpKeep[CTA_THREADS/32];
+    __shared__ int s_warpKeep[WARPS];
+    __shared__ int s_sub[WARPS][SUB_CAP];
+    __shared__ int s_subEnd[OVERLAP ? WARPS : 1][OVERLAP ? SUB_GROUPS : 1];
     int *list = P.blockList+size_t(blockIdx.x)*P.listPerCta;
     unsigned long long *caps = P.blockCaps+size_t(blockIdx.x)*P.capStride;
     double localStore[OVERLAP ? B200_LOCAL_CONTOURS*StoreLayout<MODE>::PER_CONTOUR : 1];
+    const unsigned lane = threadIdx.x&31, warp = threadIdx.x>>5;
     int stagedGlyph = -1;
     for (;;) {
         __syncthreads();
@@ -272,26 +307,30 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
             __syncthreads();
         }
         const SegRec *recs = P.bigRecs+s_g.recBase;
+        const CullRec *cull = P.bigCull+s_g.recBase;
+        const PerpRec *perp = P.bigPerp+s_g.recBase;
         const int nRec = int(s_g.s1-s_g.s0);
         const int w = s_g.w, h = s_g.h;
         const int blocksX = (w+BLOCK_W-1)/BLOCK_W;
         const int bx0 = int(td.pix0%unsigned(blocksX))*BLOCK_W, by0 = int(td.pix0/unsigned(blocksX))*BLOCK_H;
+        const double slack = 1e-12*(fabs(s_g.tx)+fabs(s_g.ty));
         // block centre and half diagonal in shape units (texel centres span +-(BLOCK-1)/2 pixels around the centre)
         const double cpx = s_g.x0+bx0+.5*BLOCK_W;
         const double cpy = s_g.y0+(s_g.flip ? h-by0-.5*BLOCK_H : by0+.5*BLOCK_H);
         const d2 c = mk(cpx/s_g.sx-s_g.tx, cpy/s_g.sy-s_g.ty);
         const double hx = .5*(BLOCK_W-1)/fabs(s_g.sx), hy = .5*(BLOCK_H-1)/fabs(s_g.sy);
-        const double hd = sqrt(hx*hx+hy*hy)*(1+1e-9)+1e-12*(fabs(c.x)+fabs(c.y)+fabs(s_g.tx)+fabs(s_g.ty));
+        const double hd = sqrt(hx*hx+hy*hy)*(1+1e-9)+1e-12*(fabs(c.x)+fabs(c.y))+slack;
 
-        // ---- phase 1: capT per (contour | shape, channel)
+        // ---- level 1, phase 1: capT per (contour | shape, channel)
         const int nGroups = OVERLAP ? int(s_g.c1-s_g.c0) : 1;
         for (int i = threadIdx.x; i < nGroups*NCH; i += CTA_THREADS)
             caps[i] = ~0ull;
         __syncthreads();
         for (int j = threadIdx.x; j < nRec; j += CTA_THREADS) {
-            const int mask = (MODE == 1 || MODE == 2) ? 1 : recs[j].color;
-            const int grp = OVERLAP ? recs[j].contour : 0;
-            d2 v = c-recs[j].p0;
+            const CullRec cr = cull[j];
+            const int mask = (MODE == 1 || MODE == 2) ? 1 : cr.color;
+            const int grp = OVERLAP ? cr.contour : 0;
+            d2 v = c-cr.p0;
             unsigned long long q = (unsigned long long) __double_as_longlong(dot(v, v));      // >= 0: bit patterns order like values
             #pragma unroll
             for (int k = 0; k < NCH; ++k)
@@ -299,36 +338,30 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
                     atomicMin(&caps[grp*NCH+k], q);
         }
         __syncthreads();
-        // ---- phase 2: ordered list of the records that can matter in this block
+        // ---- level 1, phase 2: ordered list of the records that can matter in this block
         int nList = 0;
         for (int base = 0; base < nRec; base += CTA_THREADS) {
             const int j = base+int(threadIdx.x);
             bool keep = false;
             if (j < nRec) {
-                const int mask = (MODE == 1 || MODE == 2) ? 1 : recs[j].color;
-                const int grp = OVERLAP ? recs[j].contour : 0;
+                const CullRec cr = cull[j];
+                const int mask = (MODE == 1 || MODE == 2) ? 1 : cr.color;
+                const int grp = OVERLAP ? cr.contour : 0;
                 double needT = 0;
                 #pragma unroll
                 for (int k = 0; k < NCH; ++k)
                     if (mask&(1<<k))
                         needT = dmax(needT, sqrt(__longlong_as_double((long long) caps[grp*NCH+k])));
                 needT = (needT+hd)*(1+1e-8);
-                d2 v = c-recs[j].bc;
-                const double reach = needT+recs[j].br+hd;
-                keep = !(dot(v, v) > reach*reach*(1+1e-8));
-                if (MODE != 1 && !keep) {
-                    const double lim = needT+hd;
-                    keep = !(fabs(cross(c-recs[j].p0, recs[j].aDir)) > lim) || !(fabs(cross(c-recs[j].pEnd, recs[j].bDir)) > lim);
-                }
+                keep = region_keeps<MODE>(cr, perp, j, c, hd, needT);
             }
             const unsigned ballot = __ballot_sync(0xffffffffu, keep);
-            const unsigned lane = threadIdx.x&31, warp = threadIdx.x>>5;
             if (lane == 0)
                 s_warpKeep[warp] = __popc(ballot);
             __syncthreads();
             int before = 0, total = 0;
             #pragma unroll
-            for (int k = 0; k < CTA_THREADS/32; ++k) {
+            for (int k = 0; k < WARPS; ++k) {
                 const int n = s_warpKeep[k];
                 if (k < int(warp)) before += n;
                 total += n;
@@ -342,33 +375,29 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
         // group ends: position i closes a contour's run when the next listed record belongs to another contour; the runs are
         // numbered by counting the closing positions before them (ordered compaction again, 256 positions per round)
         int *groupEnd = list+P.listStride;
+        int nListGroups = 1;
         if (OVERLAP) {
-            int nGroupsListed = 0;
+            nListGroups = 0;
             for (int base = 0; base < nList; base += CTA_THREADS) {
                 const int i = base+int(threadIdx.x);
-                const bool closes = i < nList && (i == nList-1 || recs[list[i+1]].contour != recs[list[i]].contour);
+                const bool closes = i < nList && (i == nList-1 || cull[list[i+1]].contour != cull[list[i]].contour);
                 const unsigned ballot = __ballot_sync(0xffffffffu, closes);
-                const unsigned lane = threadIdx.x&31, warp = threadIdx.x>>5;
                 if (lane == 0)
                     s_warpKeep[warp] = __popc(ballot);
                 __syncthreads();
                 int before = 0, total = 0;
                 #pragma unroll
-                for (int k = 0; k < CTA_THREADS/32; ++k) {
+                for (int k = 0; k < WARPS; ++k) {
                     const int n = s_warpKeep[k];
                     if (k < int(warp)) before += n;
                     total += n;
                 }
                 if (closes)
-                    groupEnd[nGroupsListed+before+__popc(ballot&((1u<<lane)-1u))] = i+1;
-                nGroupsListed += total;
+                    groupEnd[nListGroups+before+__popc(ballot&((1u<<lane)-1u))] = i+1;
+                nListGroups += total;
                 __syncthreads();
             }
         }
-        ListIter it;
-        it.list = list;
-        it.groupEnd = groupEnd;
-        it.group = 0;
         ContourStore store;
         store.perContour = StoreLayout<MODE>::PER_CONTOUR;
         if (OVERLAP && s_g.nonEmptyContours > B200_LOCAL_CONTOURS) {
@@ -378,18 +407,90 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
             store.base = localStore;
             store.stride = 1;
         }
-        // ---- phase 3: the texels; a warp takes an 8x4 sub-block per pass, like k1_distance_field
+        // ---- the texels; a warp takes an 8x4 sub-block per pass, like k1_distance_field
         for (int pass = 0; pass < BLOCK_H/ROWS; ++pass) {
-            const unsigned warp = threadIdx.x>>5, lane = threadIdx.x&31;
-            const int xl = int(warp%(BLOCK_W/8))*8+int(lane&7);
-            const int yl = int(warp/(BLOCK_W/8))*4+int(lane>>3);         // row inside the pass: 0 .. ROWS-1
+            const int sx0 = int(warp%(BLOCK_W/8))*8, sy0 = pass*ROWS+int(warp/(BLOCK_W/8))*4;      // sub-block origin inside the block
+            // ---- level 2: the warp's sub-list for its sub-block (warp-synchronous; no CTA barrier inside)
+            int nSub = 0, nSubGroups = 0;
+            bool overflow = false;
+            {
+                const double scx = s_g.x0+bx0+sx0+4.0;
+                const double scy = s_g.y0+(s_g.flip ? h-(by0+sy0)-2.0 : by0+sy0+2.0);
+                const d2 sc = mk(scx/s_g.sx-s_g.tx, scy/s_g.sy-s_g.ty);
+                const double shx = 3.5/fabs(s_g.sx), shy = 1.5/fabs(s_g.sy);
+                const double shd = sqrt(shx*shx+shy*shy)*(1+1e-9)+1e-12*(fabs(sc.x)+fabs(sc.y))+slack;
+                for (int g = 0; g < nListGroups; ++g) {
+                    const int i0 = OVERLAP ? (g ? groupEnd[g-1] : 0) : 0;
+                    const int i1 = OVERLAP ? groupEnd[g] : nList;
+                    double capsq[NCH];
+                    #pragma unroll
+                    for (int k = 0; k < NCH; ++k)
+                        capsq[k] = DBL_MAX;
+                    for (int i = i0+int(lane); i < i1; i += 32) {
+                        const CullRec cr = cull[list[i]];
+                        const int mask = (MODE == 1 || MODE == 2) ? 1 : cr.color;
+                        d2 v = sc-cr.p0;
+                        const double q = dot(v, v);
+                        #pragma unroll
+                        for (int k = 0; k < NCH; ++k)
+                            if (mask&(1<<k))
+                                capsq[k] = dmin(capsq[k], q);
+                    }
+                    #pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        #pragma unroll
+                        for (int d = 16; d > 0; d >>= 1)
+                            capsq[k] = dmin(capsq[k], __shfl_xor_sync(0xffffffffu, capsq[k], d));
+                        capsq[k] = sqrt(capsq[k]);      // (DBL_MAX for a channel without records: never consulted)
+                    }
+                    const int before = nSub;
+                    for (int ib = i0; ib < i1; ib += 32) {
+                        const int i = ib+int(lane);
+                        bool keep = false;
+                        int j = 0;
+                        if (i < i1) {
+                            j = list[i];
+                            const CullRec cr = cull[j];
+                            const int mask = (MODE == 1 || MODE == 2) ? 1 : cr.color;
+                            double needT = 0;
+                            #pragma unroll
+                            for (int k = 0; k < NCH; ++k)
+                                if (mask&(1<<k))
+                                    needT = dmax(needT, capsq[k]);
+                            needT = (needT+shd)*(1+1e-8);
+                            keep = region_keeps<MODE>(cr, perp, j, sc, shd, needT);
+                        }
+                        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+                        const int pos = nSub+__popc(ballot&((1u<<lane)-1u));
+                        if (keep && pos < SUB_CAP)
+                            s_sub[warp][pos] = j;
+                        nSub += __popc(ballot);
+                    }
+                    if (OVERLAP && nSub > before) {
+                        if (nSubGroups < SUB_GROUPS) {
+                            if (lane == 0)
+                                s_subEnd[warp][nSubGroups] = nSub;
+                        } else
+                            overflow = true;
+                        ++nSubGroups;
+                    }
+                }
+                overflow = overflow || nSub > SUB_CAP;
+                __syncwarp();
+            }
+            ListIter it;
+            it.list = overflow ? list : s_sub[warp];
+            it.groupEnd = overflow ? groupEnd : s_subEnd[OVERLAP ? warp : 0];
+            it.group = 0;
+            const int nWalk = overflow ? nList : nSub;
+            const int xl = sx0+int(lane&7);
+            const int yl = sy0-pass*ROWS+int(lane>>3);         // row inside the pass: 0 .. ROWS-1
             const int x = bx0+xl, yOut = by0+pass*ROWS+yl;
             if (x < w && yOut < h) {
                 const int y = s_g.flip ? h-1-yOut : yOut;
                 d2 p = mk((s_g.x0+x+.5)/s_g.sx-s_g.tx, (s_g.y0+y+.5)/s_g.sy-s_g.ty);
                 double dist[NOUT];
-                it.group = 0;
-                shape_distance_over<MODE, OVERLAP>(recs, nList, it, p, store, dist);
+                shape_distance_over<MODE, OVERLAP>(recs, nWalk, it, p, store, dist);
                 #pragma unroll
                 for (int k = 0; k < NOUT; ++k)
                     s_out[(yl*BLOCK_W+xl)*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));
