@@ -24,7 +24,7 @@ struct TileDesc { unsigned glyph, pix0; };
 
 // Compact copies of the fields the tile-level culling of big shapes reads (48 B each instead of a 352 B SegRec)
 struct CullRec { d2 bc; double br; int color, contour; d2 p0; };
-struct PerpRec { d2 pEnd, aDir, bDir; };
+struct PerpRec { d2 pEnd, aDir, bDir, aBis, bBis; };
 
 struct KernelParams {
     RawShapes raw;
@@ -84,7 +84,7 @@ __global__ void k0_prepare_big(RawShapes raw, const GlyphDesc *glyphs, const int
             c.bc = r.bc; c.br = r.br; c.color = r.color; c.contour = r.contour; c.p0 = r.p0;
             cull[size_t(g.recBase)+j] = c;
             PerpRec q;
-            q.pEnd = r.pEnd; q.aDir = r.aDir; q.bDir = r.bDir;
+            q.pEnd = r.pEnd; q.aDir = r.aDir; q.bDir = r.bDir; q.aBis = r.aBis; q.bBis = r.bBis;
             perp[size_t(g.recBase)+j] = q;
         }
     }
@@ -253,7 +253,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
 //   |p - p0| <= |c - p0| + hd.  With needT = max over the record's channels of capT[k] >= need(p):
 //     * |c - bc| - hd - br > needT   =>  |p - bc| > br + need(p)                     => culled at p;
 //     * | cross(c - p0, aDir) | - hd > needT  =>  |pdA(p)| > need(p)                 => candidate A rejected (aDir is a unit
-//       vector or zero, so pdA is 1-Lipschitz); same for B with pEnd, bDir.
+//       vector or zero, so pdA is 1-Lipschitz); same for B with pEnd, bDir.  A candidate is also rejected when one of its
+//       domain tests (dot(ap, aBis) > 0, -dot(ap, aDir) > 0; B: -dot(bp, bBis) > 0, dot(bp, bDir) > 0) fails by more than
+//       hd at c, since then it fails at every p of R.
 //   All comparisons carry a relative slack of 1e-8 (rounding is ~1e-16) and NaNs compare as "keep".
 // The lists preserve the evaluation order, so ties resolve exactly as in the full walk.  Results are bit-identical.
 #define BLOCK_W 32
@@ -268,8 +270,14 @@ __device__ __forceinline__ bool region_keeps(const CullRec &cr, const PerpRec *p
     bool keep = !(dot(v, v) > reach*reach*(1+1e-8));
     if (MODE != 1 && !keep) {
         const double lim = needT+hd;
+        // a candidate also has to pass the domain tests of sel_add_edge somewhere in the region: dot(ap, aBis) > 0 and
+        // -dot(ap, aDir) > 0 (B: -dot(bp, bBis) > 0 and dot(bp, bDir) > 0); all four are 1-Lipschitz in p
         const PerpRec q = perp[j];
-        keep = !(fabs(cross(c-cr.p0, q.aDir)) > lim) || !(fabs(cross(c-q.pEnd, q.bDir)) > lim);
+        const double hs = hd*(1+1e-8);
+        const d2 ap = c-cr.p0, bp = c-q.pEnd;
+        const bool a = !(fabs(cross(ap, q.aDir)) > lim) && !(dot(ap, q.aBis) < -hs) && !(dot(ap, q.aDir) > hs);
+        const bool b = !(fabs(cross(bp, q.bDir)) > lim) && !(dot(bp, q.bBis) > hs) && !(dot(bp, q.bDir) < -hs);
+        keep = a || b;
     }
     return keep;
 }
