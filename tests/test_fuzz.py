@@ -56,7 +56,8 @@ def test_cuda_matches_reference_digests(ctx, port):
                 want = port.generate(mode, cb, pts, od, cl, xf, w, h, ocfg)
                 if mode == "sdf" and not np.allclose(np.abs(f - 0.5), np.abs(want - 0.5), rtol=0, atol=1e-6):
                     bad.append((seed, fam, key, "magnitude"))
-                if not np.array_equal(np.isfinite(f), np.isfinite(want)):       # (a channel without edges is -inf in both)
+                # a channel without edges is -inf in both (error correction may then replace noise-dependent texels by the median)
+                if key.endswith("ec0") and not np.array_equal(np.isfinite(f), np.isfinite(want)):
                     bad.append((seed, fam, key, "non-finite"))
                 continue
             if digest(f) != GOLDEN[f"{seed}/{key}"]:
