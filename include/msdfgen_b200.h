@@ -167,6 +167,16 @@ int b200msdf_sign_correction(b200msdf_ctx *ctx, int channels, const b200msdf_sha
 int b200msdf_rasterize(b200msdf_ctx *ctx, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
                        int transform_per_glyph, const b200msdf_bitmap *outputs, int fill_rule);
 
+/* renderSDF(output, sdf, sdfPxRange, sdThreshold) (core/render-sdf.h:11-16, render-sdf.cpp:14-173): reconstructs the shape's
+ * appearance from a distance field by bilinear sampling.  (out_channels <- sdf_channels) is one of 1<-1, 3<-1, 1<-3, 3<-3, 1<-4,
+ * 4<-4 like the reference's overloads; px_range_lower == px_range_upper selects the hard threshold.  Orientation flags are
+ * ignored, as in the reference. */
+int b200msdf_render_sdf(b200msdf_ctx *ctx, const b200msdf_bitmap *output, int out_channels, const b200msdf_bitmap *sdf, int sdf_channels,
+                        double px_range_lower, double px_range_upper, float sd_threshold);
+
+/* simulate8bit (core/render-sdf.h:19-21): snaps every float of the bitmap to the value an 8-bit image would hold. */
+int b200msdf_simulate_8bit(b200msdf_ctx *ctx, const b200msdf_bitmap *bitmap, int channels);
+
 /* ---- HBM-resident batches (asynchronous on the context's stream) ---------------------------------------------------- */
 
 /* Uploads shapes + per-glyph geometry and allocates outputs. dims: [2] shared (w,h) or [2*n_glyphs] (dims_per_glyph != 0).

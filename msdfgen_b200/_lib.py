@@ -17,7 +17,7 @@ EXPORTS = [
     "b200msdf_version", "b200msdf_last_error", "b200msdf_default_config", "b200msdf_create", "b200msdf_destroy",
     "b200msdf_set_stream", "b200msdf_synchronize", "b200msdf_launch_count", "b200msdf_host_alloc", "b200msdf_host_free",
     "b200msdf_generate", "b200msdf_generate_batch", "b200msdf_generate_batch_u8", "b200msdf_error_correction", "b200msdf_fast_error_correction",
-    "b200msdf_sign_correction", "b200msdf_rasterize", "b200msdf_batch_sign_correction",
+    "b200msdf_sign_correction", "b200msdf_rasterize", "b200msdf_batch_sign_correction", "b200msdf_render_sdf", "b200msdf_simulate_8bit",
     "b200msdf_batch_upload", "b200msdf_batch_upload_regions", "b200msdf_batch_launch", "b200msdf_batch_launch_stages", "b200msdf_batch_device_output", "b200msdf_batch_device_stencil",
     "b200msdf_batch_output_floats", "b200msdf_batch_glyph_offset", "b200msdf_batch_download", "b200msdf_batch_free",
 ]
@@ -86,6 +86,8 @@ def load():
     lib.b200msdf_sign_correction.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(Bitmap), C.c_float, i32]
     lib.b200msdf_rasterize.argtypes = [vp, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(Bitmap), i32]
     lib.b200msdf_batch_sign_correction.argtypes = [vp, vp, C.c_float, i32]
+    lib.b200msdf_render_sdf.argtypes = [vp, C.POINTER(Bitmap), i32, C.POINTER(Bitmap), i32, C.c_double, C.c_double, C.c_float]
+    lib.b200msdf_simulate_8bit.argtypes = [vp, C.POINTER(Bitmap), i32]
     lib.b200msdf_batch_upload.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(C.c_int32), i32,
                                           C.POINTER(C.c_uint8), C.POINTER(vp)]
     lib.b200msdf_batch_upload_regions.argtypes = [vp, i32, C.POINTER(Shapes), C.POINTER(Transform), i32, C.POINTER(C.c_int32), i32,

@@ -245,6 +245,19 @@ class Context:
         _lib.check(self.lib.b200msdf_rasterize(self.h, C.byref(s), xf, per, bms, fill_rule))
         return outputs
 
+    def render_sdf(self, output, sdf, sdf_px_range=(0.0, 0.0), sd_threshold=0.5):
+        """renderSDF (core/render-sdf.h:11-16): output float32 [oh,ow,NO] <- sdf float32 [h,w,NI]; sdf_px_range a number or (lower, upper)."""
+        lo, hi = (-0.5 * sdf_px_range, 0.5 * sdf_px_range) if np.isscalar(sdf_px_range) else sdf_px_range     # Range(symmetricalWidth)
+        bo, bs = _bitmap(output), _bitmap(sdf)
+        _lib.check(self.lib.b200msdf_render_sdf(self.h, C.byref(bo), output.shape[2], C.byref(bs), sdf.shape[2], float(lo), float(hi), float(sd_threshold)))
+        return output
+
+    def simulate_8bit(self, bitmap):
+        """simulate8bit (core/render-sdf.h:19-21), in place."""
+        bm = _bitmap(bitmap)
+        _lib.check(self.lib.b200msdf_simulate_8bit(self.h, C.byref(bm), bitmap.shape[2]))
+        return bitmap
+
     # ---- HBM-resident batches --------------------------------------------------------------------------------------
     def upload(self, mode, shapes: FlatShapes, transformations, dims, out_ydown=None, origins=None):
         """origins: (x0, y0) pixel origin(s) of the output block(s) inside their full image (region batches, SDF/PSDF or EC off)."""
@@ -359,6 +372,16 @@ def distanceSignCorrection(sdf, shape, projection, sdfZeroValue=0.5, fillRule=FI
 def rasterize(output, shape, projection, fillRule=FILL_NONZERO, **kw):
     """core/rasterization.h:12"""
     return default_context().rasterize([output], shape, projection, fillRule, **kw)[0]
+
+
+def renderSDF(output, sdf, sdfPxRange=0.0, sdThreshold=0.5):
+    """core/render-sdf.h:11-16"""
+    return default_context().render_sdf(output, sdf, sdfPxRange, sdThreshold)
+
+
+def simulate8bit(bitmap):
+    """core/render-sdf.h:19-21"""
+    return default_context().simulate_8bit(bitmap)
 
 
 def msdfFastDistanceErrorCorrection(sdf, transformation, minDeviationRatio=DEFAULT_RATIO):

@@ -4,6 +4,7 @@
 #include "../../include/msdfgen_b200.h"
 #include "error_correction.cuh"
 #include "scanline.cuh"
+#include "render.cuh"
 
 #include <climits>
 #include <cstdarg>
@@ -1019,6 +1020,99 @@ int b200msdf_sign_correction(b200msdf_ctx *ctx, int channels, const b200msdf_sha
 int b200msdf_rasterize(b200msdf_ctx *ctx, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
                        const b200msdf_bitmap *outputs, int fill_rule) {
     return scanline_common(ctx, 1, shapes, xf, xfPerGlyph, outputs, 0.f, fill_rule, true);
+}
+
+// Host image <-> packed device block helpers of the render entry points (pool buffers: field = input, out = output)
+static int upload_image(b200msdf_ctx *ctx, DevBuf &dst, const b200msdf_bitmap *bm, int N) {
+    size_t floats = (size_t) bm->width*bm->height*N;
+    int rc = dst.reserve(floats*4+64);
+    if (rc) return rc;
+    if ((rc = ctx->pinIn.reserve(floats*4+64))) return rc;
+    float *h = static_cast<float *>(ctx->pinIn.p);
+    for (int r = 0; r < bm->height; ++r)
+        memcpy(h+(size_t) r*bm->width*N, bm->pixels+(ptrdiff_t) bm->row_stride*r, sizeof(float)*(size_t) bm->width*N);
+    CUDA_TRY(cudaMemcpyAsync(dst.p, h, floats*4, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+static int download_image(b200msdf_ctx *ctx, const DevBuf &src, const b200msdf_bitmap *bm, int N) {
+    size_t floats = (size_t) bm->width*bm->height*N;
+    int rc = ctx->pinOut.reserve(floats*4+64);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx->pinOut.p, src.p, floats*4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    const float *h = static_cast<const float *>(ctx->pinOut.p);
+    for (int r = 0; r < bm->height; ++r)
+        memcpy(bm->pixels+(ptrdiff_t) bm->row_stride*r, h+(size_t) r*bm->width*N, sizeof(float)*(size_t) bm->width*N);
+    return 0;
+}
+
+int b200msdf_render_sdf(b200msdf_ctx *ctx, const b200msdf_bitmap *output, int outN, const b200msdf_bitmap *sdf, int sdfN,
+                        double lower, double upper, float threshold) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!output || !sdf)
+        return fail(B200MSDF_ERR_ARG, "null bitmap");
+    if (!((outN == 1 && (sdfN == 1 || sdfN == 3 || sdfN == 4)) || (outN == 3 && (sdfN == 1 || sdfN == 3)) || (outN == 4 && sdfN == 4)))
+        return fail(B200MSDF_ERR_ARG, "renderSDF has no overload for %d <- %d channels", outN, sdfN);
+    if ((rc = check_bitmaps(output, 1)) || (rc = check_bitmaps(sdf, 1))) return rc;
+    if ((size_t) output->width*output->height == 0)
+        return 0;
+    if ((size_t) sdf->width*sdf->height == 0)
+        return fail(B200MSDF_ERR_ARG, "empty distance field");
+    b200msdf_batch *b = &ctx->pool;
+    if ((rc = upload_image(ctx, b->field, sdf, sdfN))) return rc;
+    if ((rc = b->out.reserve((size_t) output->width*output->height*outN*4+64))) return rc;
+    RenderParams R;
+    R.sdf = b->field.as<float>();
+    R.out = b->out.as<float>();
+    R.sw = sdf->width; R.sh = sdf->height; R.ow = output->width; R.oh = output->height;
+    R.scaleX = (double) sdf->width/output->width;
+    R.scaleY = (double) sdf->height/output->height;
+    R.hard = lower == upper;
+    R.threshold = threshold;
+    R.bias = .5f-threshold;
+    R.mapScale = 1; R.mapTranslate = 0;
+    if (!R.hard) {
+        // sdfPxRange *= (output.width+output.height)/(sdf.width+sdf.height); DistanceMapping::inverse(range)
+        double f = (double) (output->width+output->height)/(sdf->width+sdf->height);
+        lower *= f;
+        upper *= f;
+        double width = upper-lower;
+        R.mapScale = width;
+        R.mapTranslate = lower/(width ? width : 1);
+    }
+    size_t total = (size_t) output->width*output->height;
+    int grid = (int) ((total+CTA_THREADS-1)/CTA_THREADS < (size_t) ctx->numSMs*8 ? (total+CTA_THREADS-1)/CTA_THREADS : (size_t) ctx->numSMs*8);
+    switch (outN*8+sdfN) {
+        case 1*8+1: k6_render_sdf<1, 1><<<grid, CTA_THREADS, 0, ctx->stream>>>(R); break;
+        case 3*8+1: k6_render_sdf<1, 3><<<grid, CTA_THREADS, 0, ctx->stream>>>(R); break;
+        case 1*8+3: k6_render_sdf<3, 1><<<grid, CTA_THREADS, 0, ctx->stream>>>(R); break;
+        case 3*8+3: k6_render_sdf<3, 3><<<grid, CTA_THREADS, 0, ctx->stream>>>(R); break;
+        case 1*8+4: k6_render_sdf<4, 1><<<grid, CTA_THREADS, 0, ctx->stream>>>(R); break;
+        default:    k6_render_sdf<4, 4><<<grid, CTA_THREADS, 0, ctx->stream>>>(R); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    ++ctx->launches;
+    return download_image(ctx, b->out, output, outN);
+}
+
+int b200msdf_simulate_8bit(b200msdf_ctx *ctx, const b200msdf_bitmap *bitmap, int channels) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (!bitmap || channels < 1 || channels > 4)
+        return fail(B200MSDF_ERR_ARG, "bad bitmap / channel count");
+    if ((rc = check_bitmaps(bitmap, 1))) return rc;
+    size_t n = (size_t) bitmap->width*bitmap->height*channels;
+    if (!n)
+        return 0;
+    b200msdf_batch *b = &ctx->pool;
+    if ((rc = upload_image(ctx, b->out, bitmap, channels))) return rc;
+    int grid = (int) ((n+CTA_THREADS-1)/CTA_THREADS < (size_t) ctx->numSMs*8 ? (n+CTA_THREADS-1)/CTA_THREADS : (size_t) ctx->numSMs*8);
+    k6_simulate_8bit<<<grid, CTA_THREADS, 0, ctx->stream>>>(b->out.as<float>(), n);
+    CUDA_TRY(cudaGetLastError());
+    ++ctx->launches;
+    return download_image(ctx, b->out, bitmap, channels);
 }
 
 int b200msdf_batch_sign_correction(b200msdf_ctx *ctx, b200msdf_batch *batch, float sdf_zero_value, int fill_rule) {

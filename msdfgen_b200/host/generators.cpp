@@ -254,6 +254,38 @@ void signCorrectOne(const BitmapSection<float, N> &sdf, const Shape &shape, cons
         report(rc);
 }
 
+template <int NO, int NI>
+void renderOne(const BitmapSection<float, NO> &output, const BitmapConstSection<float, NI> &sdf, Range sdfPxRange, float sdThreshold) {
+    b200msdf_ctx *ctx = context();
+    if (!ctx)
+        return;
+    b200msdf_bitmap o = marshal(output);
+    b200msdf_bitmap i;
+    i.pixels = const_cast<float *>(sdf.pixels);       // read only
+    i.width = sdf.width; i.height = sdf.height;
+    i.row_stride = sdf.rowStride;
+    i.y_downward = sdf.yOrientation == Y_DOWNWARD;
+    int rc = b200msdf_render_sdf(ctx, &o, NO, &i, NI, sdfPxRange.lower, sdfPxRange.upper, sdThreshold);
+    if (rc)
+        report(rc);
+}
+
+template <int N>
+void snapOne(const BitmapSection<float, N> &bitmap) {
+    b200msdf_ctx *ctx = context();
+    if (!ctx)
+        return;
+    // the reference walks width*height*N consecutive floats from the first pixel (render-sdf.cpp:175-191)
+    b200msdf_bitmap b;
+    b.pixels = bitmap.pixels;
+    b.width = bitmap.width; b.height = bitmap.height;
+    b.row_stride = N*bitmap.width;
+    b.y_downward = 0;
+    int rc = b200msdf_simulate_8bit(ctx, &b, N);
+    if (rc)
+        report(rc);
+}
+
 }  // namespace
 
 // ---- generators ------------------------------------------------------------------------------------------------------------
@@ -362,6 +394,18 @@ void distanceSignCorrection(BitmapSection<float, 4> sdf, const Shape &shape, con
 void distanceSignCorrection(const BitmapSection<float, 1> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule) { signCorrectOne(sdf, shape, Projection(scale, translate), .5f, fillRule); }
 void distanceSignCorrection(const BitmapSection<float, 3> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule) { signCorrectOne(sdf, shape, Projection(scale, translate), .5f, fillRule); }
 void distanceSignCorrection(const BitmapSection<float, 4> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule) { signCorrectOne(sdf, shape, Projection(scale, translate), .5f, fillRule); }
+
+// ---- preview rendering -----------------------------------------------------------------------------------------------------
+
+void renderSDF(const BitmapSection<float, 1> &output, const BitmapConstSection<float, 1> &sdf, Range sdfPxRange, float sdThreshold) { renderOne(output, sdf, sdfPxRange, sdThreshold); }
+void renderSDF(const BitmapSection<float, 3> &output, const BitmapConstSection<float, 1> &sdf, Range sdfPxRange, float sdThreshold) { renderOne(output, sdf, sdfPxRange, sdThreshold); }
+void renderSDF(const BitmapSection<float, 1> &output, const BitmapConstSection<float, 3> &sdf, Range sdfPxRange, float sdThreshold) { renderOne(output, sdf, sdfPxRange, sdThreshold); }
+void renderSDF(const BitmapSection<float, 3> &output, const BitmapConstSection<float, 3> &sdf, Range sdfPxRange, float sdThreshold) { renderOne(output, sdf, sdfPxRange, sdThreshold); }
+void renderSDF(const BitmapSection<float, 1> &output, const BitmapConstSection<float, 4> &sdf, Range sdfPxRange, float sdThreshold) { renderOne(output, sdf, sdfPxRange, sdThreshold); }
+void renderSDF(const BitmapSection<float, 4> &output, const BitmapConstSection<float, 4> &sdf, Range sdfPxRange, float sdThreshold) { renderOne(output, sdf, sdfPxRange, sdThreshold); }
+void simulate8bit(const BitmapSection<float, 1> &bitmap) { snapOne(bitmap); }
+void simulate8bit(const BitmapSection<float, 3> &bitmap) { snapOne(bitmap); }
+void simulate8bit(const BitmapSection<float, 4> &bitmap) { snapOne(bitmap); }
 
 // ---- B200 additions --------------------------------------------------------------------------------------------------------
 

@@ -237,6 +237,28 @@ class Oracle:
             raise RuntimeError("rasterize failed")
         return out
 
+    def render_sdf(self, sdf, ow, oh, out_channels, px_range=(0.0, 0.0), threshold=0.5):
+        """renderSDF (core/render-sdf.h:11-16): sdf float32 [h,w,N] -> float32 [oh,ow,out_channels]."""
+        sdf = np.ascontiguousarray(sdf, dtype=np.float32)
+        sh, sw, n = sdf.shape
+        out = np.full((oh, ow, out_channels), np.nan, np.float32)
+        fn = getattr(self.lib, self.pfx + "render_sdf")
+        fn.restype = C.c_int
+        rc = fn(C.c_int(out_channels), _p(out, C.c_float), C.c_int(ow), C.c_int(oh), C.c_int(n), _p(sdf, C.c_float), C.c_int(sw), C.c_int(sh),
+                C.c_double(px_range[0]), C.c_double(px_range[1]), C.c_float(threshold))
+        if rc:
+            raise RuntimeError("render_sdf: unsupported channel combination")
+        return out
+
+    def simulate_8bit(self, bitmap):
+        """simulate8bit (core/render-sdf.h:19-21) on a copy."""
+        b = np.array(bitmap, dtype=np.float32, order="C", copy=True)
+        h, w, n = b.shape
+        fn = getattr(self.lib, self.pfx + "simulate_8bit")
+        fn.restype = None
+        fn(_p(b, C.c_float), C.c_int(w), C.c_int(h), C.c_int(n))
+        return b
+
     # -- pieces ------------------------------------------------------------------------------------------------------
     def distance(self, mode, overlap, cbegin, points, orders, colors, pts):
         """Raw fp64 shape distance (oneShotDistance) at arbitrary points -> float64[nPts, N]."""

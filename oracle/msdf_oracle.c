@@ -1260,6 +1260,80 @@ int oracle_sign_correction(int N, int nContours, const uint32_t *cbegin, const d
     return 0;
 }
 
+/* ---- renderSDF / simulate8bit (core/render-sdf.cpp, bitmap-interpolation.hpp:11-27) ---- */
+static int iclamp(int n, int b) { return n >= 0 && n <= b ? n : (n > 0)*b; }                 /* clamp(n, b), arithmetics.hpp:40-43 */
+static double dclamp(double n, double b) { return n >= 0 && n <= b ? n : (double) (n > 0)*b; }
+static float fmixd(float a, float b, double w) { return (float) ((1.0-w)*a+w*b); }           /* mix<float, double> */
+
+static void interpolate_n(float *out, const float *bitmap, int w, int h, int N, double px, double py) {
+    px = dclamp(px, (double) w);
+    py = dclamp(py, (double) h);
+    px -= .5;
+    py -= .5;
+    int l = (int) floor(px), b = (int) floor(py);
+    int r = l+1, t = b+1;
+    double lr = px-l, bt = py-b;
+    l = iclamp(l, w-1), r = iclamp(r, w-1);
+    b = iclamp(b, h-1), t = iclamp(t, h-1);
+    for (int i = 0; i < N; ++i)
+        out[i] = fmixd(fmixd(bitmap[((size_t) b*w+l)*N+i], bitmap[((size_t) b*w+r)*N+i], lr), fmixd(bitmap[((size_t) t*w+l)*N+i], bitmap[((size_t) t*w+r)*N+i], lr), bt);
+}
+
+/* renderSDF for (outN <- sdfN) in {1<-1, 3<-1, 1<-3, 3<-3, 1<-4, 4<-4} (render-sdf.cpp:14-173) */
+int oracle_render_sdf(int outN, float *out, int ow, int oh, int sdfN, const float *sdf, int sw, int sh, double lower, double upper, float threshold) {
+    if (!((outN == 1 && (sdfN == 1 || sdfN == 3 || sdfN == 4)) || (outN == 3 && (sdfN == 1 || sdfN == 3)) || (outN == 4 && sdfN == 4)))
+        return -1;
+    double sx = (double) sw/ow, sy = (double) sh/oh;
+    int hard = lower == upper;
+    double mScale = 1, mTranslate = 0;
+    float bias = .5f-threshold;
+    if (!hard) {
+        double f = (double) (ow+oh)/(sw+sh);
+        lower *= f;
+        upper *= f;
+        double width = upper-lower;                     /* DistanceMapping::inverse(range), DistanceMapping.cpp:6-9 */
+        mScale = width;
+        mTranslate = lower/(width ? width : 1);
+    }
+    for (int y = 0; y < oh; ++y)
+        for (int x = 0; x < ow; ++x) {
+            float sd[4];
+            interpolate_n(sd, sdf, sw, sh, sdfN, sx*(x+.5), sy*(y+.5));
+            float v[4];
+            int nv = sdfN;
+            if (outN == 1 && sdfN >= 3) {
+                v[0] = fmedian(sd[0], sd[1], sd[2]);
+                nv = 1;
+            } else
+                for (int i = 0; i < sdfN; ++i) v[i] = sd[i];
+            for (int i = 0; i < nv; ++i) {
+                if (hard)
+                    v[i] = (float) (v[i] >= threshold);
+                else {
+                    double m = mScale*((double) (v[i]+bias)+mTranslate)+.5;       /* distVal */
+                    v[i] = (float) (m >= 0 && m <= 1 ? m : (double) (m > 0));
+                }
+            }
+            float *o = out+((size_t) y*ow+x)*outN;
+            if (outN == 3 && sdfN == 1)
+                o[0] = o[1] = o[2] = v[0];
+            else
+                for (int i = 0; i < outN; ++i) o[i] = v[i];
+        }
+    return 0;
+}
+
+/* simulate8bit: pixelByteToFloat(pixelFloatToByte(x)) (render-sdf.cpp:175-191, pixel-conversion.hpp:8-14) */
+void oracle_simulate_8bit(float *pixels, int w, int h, int N) {
+    size_t n = (size_t) w*h*N;
+    for (size_t i = 0; i < n; ++i) {
+        float x = pixels[i];
+        float c = x >= 0.f && x <= 1.f ? x : (float) (x > 0.f);
+        unsigned char b = (unsigned char) ~(int) (255.5f-255.f*c);
+        pixels[i] = 1.f/255.f*(float) b;
+    }
+}
+
 /* pixelFloatToByte, core/pixel-conversion.hpp:8-10 (clamp: arithmetics.hpp:34-37) */
 void oracle_pixel_float_to_byte(const float *in, uint8_t *out, size_t n) {
     for (size_t i = 0; i < n; ++i) {

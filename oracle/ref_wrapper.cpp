@@ -37,6 +37,7 @@
 #include "core/MSDFErrorCorrection.h"
 #include "core/pixel-conversion.hpp"
 #include "core/equation-solver.h"
+#include "core/render-sdf.h"
 
 using namespace msdfgen;
 
@@ -322,6 +323,22 @@ int ref_rasterize(int nContours, const uint32_t *cbegin, const double *points, c
     buildShape(shape, nContours, cbegin, points, orders, NULL, yDown);
     rasterize(BitmapSection<float, 1>(out, w, h, w, outYDown ? Y_DOWNWARD : Y_UPWARD), shape, Projection(Vector2(xf[0], xf[1]), Vector2(xf[2], xf[3])), (FillRule) fillRule);
     return 0;
+}
+
+/// renderSDF(output, sdf, sdfPxRange, sdThreshold) (core/render-sdf.h:11-16) for the six channel combinations it declares.
+int ref_render_sdf(int outN, float *out, int ow, int oh, int sdfN, const float *sdf, int sw, int sh, double lower, double upper, float threshold) {
+    Range range(lower, upper);
+    #define RENDER(NO, NI) if (outN == NO && sdfN == NI) { renderSDF(BitmapSection<float, NO>(out, ow, oh), BitmapConstSection<float, NI>(sdf, sw, sh), range, threshold); return 0; }
+    RENDER(1, 1) RENDER(3, 1) RENDER(1, 3) RENDER(3, 3) RENDER(1, 4) RENDER(4, 4)
+    #undef RENDER
+    return -1;
+}
+
+/// simulate8bit (core/render-sdf.h:19-21), in place on n floats.
+void ref_simulate_8bit(float *pixels, int w, int h, int N) {
+    if (N == 1) simulate8bit(BitmapSection<float, 1>(pixels, w, h));
+    else if (N == 3) simulate8bit(BitmapSection<float, 3>(pixels, w, h));
+    else if (N == 4) simulate8bit(BitmapSection<float, 4>(pixels, w, h));
 }
 
 void ref_pixel_float_to_byte(const float *in, uint8_t *out, size_t n) {

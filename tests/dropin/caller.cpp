@@ -117,4 +117,22 @@ int caller_scanline(int nContours, const uint32_t *cbegin, const double *pts, co
     return 0;
 }
 
+// Preview path of the command line (-testrender, main.cpp:1330-1390): generate, snap to 8 bits, render at another size.
+// out: float[2h][2w][3] render of the msdf | float[h][w] hard-threshold render of the mtsdf's median
+int caller_render(int nContours, const uint32_t *cbegin, const double *pts, const uint8_t *orders, int w, int h, float *out) {
+    Shape shape;
+    buildShape(shape, nContours, cbegin, pts, orders, 0);
+    shape.normalize();
+    edgeColoringSimple(shape, 3.0);
+    SDFTransformation t = autoframe(shape, w, h, 4.0);
+    Bitmap<float, 3> msdf(w, h);
+    generateMSDF(msdf, shape, t);
+    simulate8bit(msdf);
+    renderSDF(BitmapSection<float, 3>(out, 2*w, 2*h), msdf, Range(4.0));
+    Bitmap<float, 4> mtsdf(w, h);
+    generateMTSDF(mtsdf, shape, t);
+    renderSDF(BitmapSection<float, 1>(out+size_t(2*w)*(2*h)*3, w, h), mtsdf);
+    return 0;
+}
+
 }

@@ -18,7 +18,7 @@ arrays = {"seeds": seeds}
 for i, seed in enumerate(seeds):
     r = test_dropin._run(lib, synth_glyph(int(seed), cubic_fraction=0.2))
     arrays[f"edges{i}"] = np.int64(r["edges"])
-    for key in ("msdf", "modes", "ec", "stencil", "scanline"):
+    for key in ("msdf", "modes", "ec", "stencil", "scanline", "render"):
         arrays[f"{key}{i}"] = r[key]
 path = os.path.join(ROOT, "tests", "golden", "dropin_v1.npz")
 np.savez_compressed(path, **arrays)

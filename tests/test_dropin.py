@@ -61,6 +61,9 @@ def _run(lib, g, w=24, h=20):
     d = np.full(h * w * 9, np.nan, np.float32)
     assert lib.caller_scanline(*_args(g), C.c_int(w), C.c_int(h), d.ctypes.data_as(C.POINTER(C.c_float))) == 0
     res["scanline"] = d
+    e = np.full(4 * h * w * 3 + h * w, np.nan, np.float32)
+    assert lib.caller_render(*_args(g), C.c_int(w), C.c_int(h), e.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    res["render"] = e
     return res
 
 
@@ -87,7 +90,7 @@ def test_b200_build_matches_reference_build():
         g = synth_glyph(int(seed), cubic_fraction=0.2)
         mine = _run(b200, g)
         assert mine["edges"] == int(z[f"edges{i}"])
-        for key in ("msdf", "modes", "ec", "scanline"):
+        for key in ("msdf", "modes", "ec", "scanline", "render"):
             want = z[f"{key}{i}"]
             bits, max_abs, over = compare(mine[key], want)
             assert over == 0 and max_abs <= 1e-4, (key, seed, bits, max_abs)
