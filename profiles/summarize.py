@@ -24,14 +24,16 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__sass_branch_targets_threads_divergent.sum", "smsp__sass_branch_targets.sum"]
 
 traffic = {}
-for kernel in ("k1_distance_field", "k2_classify", "k3_exact_distance"):
+for kernel in ("k1_distance_field", "k2_classify", "k3_exact_distance", "k1_big_blocks"):
     rep = os.path.join(ROOT, "gpurun_out", f"{kernel}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
-    lines = [f"# {kernel} — ncu --set full --clock-control none (one launch of `python bench.py --steps 1 --warmup 3`, 4096 glyphs msdf 32x32)",
+    what = ("one launch of `SIZE=2048 MODE=1 python tests/_gpu_big_one.py`: the 10k-segment shape, sdf 2048x2048, overlapping combiner"
+            if kernel == "k1_big_blocks" else "one launch of `python bench.py --steps 1 --warmup 3`, 4096 glyphs msdf 32x32")
+    lines = [f"# {kernel} — ncu --set full --clock-control none ({what})",
              f"# kernel: {vals[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else kernel}", ""]
     get = {}
     for i, h in enumerate(hdr):
