@@ -339,7 +339,8 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
     b200msdf_batch *b = ctx->cur;
     if (b->nBlocks > 0) {
         int grid = 1;
-        if ((rc = grid_for(ctx, k1_big_blocks<MODE, OVERLAP>, b->nBlocks, 0, CTA_THREADS, &grid))) return rc;
+        const size_t subListBytes = (size_t) (CTA_THREADS/32)*SUB_CAP*sizeof(int);      // the warps' sub-lists (dynamic shared memory)
+        if ((rc = grid_for(ctx, k1_big_blocks<MODE, OVERLAP>, b->nBlocks, subListBytes, CTA_THREADS, &grid))) return rc;
         P.blocks = b->blocks.as<TileDesc>();
         P.nBlocks = b->nBlocks;
         P.listStride = ((size_t) b->maxBigSegs+3)&~size_t(3);
@@ -357,7 +358,7 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
         } else
             P.scratch = nullptr;
         P.counterIndex = 3;
-        k1_big_blocks<MODE, OVERLAP><<<grid, CTA_THREADS, 0, ctx->stream>>>(P);
+        k1_big_blocks<MODE, OVERLAP><<<grid, CTA_THREADS, subListBytes, ctx->stream>>>(P);
         CUDA_TRY(cudaGetLastError());
         ++ctx->launches;
     }

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
 // The lists preserve the evaluation order, so ties resolve exactly as in the full walk.  Results are bit-identical.
 #define BLOCK_W 32
 #define BLOCK_H 32
-#define SUB_CAP 1024        // record indices per warp sub-list (shared memory); overflow -> the warp walks the block list
+#define SUB_CAP 3072        // record indices per warp sub-list (dynamic shared memory); overflow -> the warp walks the block list
 #define SUB_GROUPS 256      // contour groups per warp sub-list
 
 template <int MODE>
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
     __shared__ GlyphDesc s_g;
     __shared__ int s_tile;
     __shared__ int s_warpKeep[WARPS];
-    __shared__ int s_sub[WARPS][SUB_CAP];
+    extern __shared__ int s_sub[];          // WARPS x SUB_CAP
     __shared__ int s_subEnd[OVERLAP ? WARPS : 1][OVERLAP ? SUB_GROUPS : 1];
     int *list = P.blockList+size_t(blockIdx.x)*P.listPerCta;
     unsigned long long *caps = P.blockCaps+size_t(blockIdx.x)*P.capStride;
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
                         const unsigned ballot = __ballot_sync(0xffffffffu, keep);
                         const int pos = nSub+__popc(ballot&((1u<<lane)-1u));
                         if (keep && pos < SUB_CAP)
-                            s_sub[warp][pos] = j;
+                            s_sub[warp*SUB_CAP+pos] = j;
                         nSub += __popc(ballot);
                     }
                     if (OVERLAP && nSub > before) {
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
                 __syncwarp();
             }
             ListIter it;
-            it.list = overflow ? list : s_sub[warp];
+            it.list = overflow ? list : s_sub+warp*SUB_CAP;
             it.groupEnd = overflow ? groupEnd : s_subEnd[OVERLAP ? warp : 0];
             it.group = 0;
             const int nWalk = overflow ? nList : nSub;
