@@ -14,6 +14,8 @@
 #include <unordered_map>
 #include <new>
 #include <string>
+#include <algorithm>
+#include <functional>
 #include <vector>
 
 using namespace b200;
@@ -236,6 +238,25 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
             td.pix0 = (unsigned) p0;
             (d.recBase < 0 ? b->hTiles : bigTiles).push_back(td);
         }
+    }
+    // Longest-processing-time-first: the persistent CTAs pull tiles from an atomic counter (greedy list scheduling), so handing
+    // out the expensive tiles first leaves only cheap ones for the tail.  Cost model: segments x texels of the tile (< 2^32);
+    // one 64-bit key per tile = cost in the high word, inverted position in the low word (descending sort keeps equal-cost
+    // tiles — e.g. the tiles of one glyph — in their original order).
+    if (b->hTiles.size() > 1) {
+        const size_t n = b->hTiles.size();
+        std::vector<uint64_t> keys(n);
+        for (size_t t = 0; t < n; ++t) {
+            const GlyphDesc &d = b->hGlyphs[b->hTiles[t].glyph];
+            size_t px = (size_t) d.w*(size_t) d.h-b->hTiles[t].pix0;
+            uint64_t cost = (uint64_t) (d.s1-d.s0)*(px < TILE_PIXELS ? px : (size_t) TILE_PIXELS);
+            keys[t] = (cost << 32)|(uint64_t) (0xffffffffu-(uint32_t) t);
+        }
+        std::sort(keys.begin(), keys.end(), std::greater<uint64_t>());
+        std::vector<TileDesc> sorted(n);
+        for (size_t t = 0; t < n; ++t)
+            sorted[t] = b->hTiles[0xffffffffu-(uint32_t) (keys[t]&0xffffffffu)];
+        b->hTiles.swap(sorted);
     }
     b->nSmallTiles = (int) b->hTiles.size();
     b->hTiles.insert(b->hTiles.end(), bigTiles.begin(), bigTiles.end());
