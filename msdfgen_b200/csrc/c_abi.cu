@@ -240,22 +240,27 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
         }
     }
     // Longest-processing-time-first: the persistent CTAs pull tiles from an atomic counter (greedy list scheduling), so handing
-    // out the expensive tiles first leaves only cheap ones for the tail.  Cost model: segments x texels of the tile (< 2^32);
-    // one 64-bit key per tile = cost in the high word, inverted position in the low word (descending sort keeps equal-cost
-    // tiles — e.g. the tiles of one glyph — in their original order).
+    // out the expensive tiles first leaves only cheap ones for the tail.  Cost model: segments x texels of the tile, quantised
+    // to 256 classes; a stable counting sort (O(tiles), ~10 us for 4096 tiles — this runs inside every host-buffer call) keeps
+    // equal-cost tiles, e.g. the tiles of one glyph, in their original order.
     if (b->hTiles.size() > 1) {
         const size_t n = b->hTiles.size();
-        std::vector<uint64_t> keys(n);
+        const int CLASSES = 256;
+        std::vector<uint8_t> cls(n);
+        size_t count[CLASSES+1] = { 0 };
         for (size_t t = 0; t < n; ++t) {
             const GlyphDesc &d = b->hGlyphs[b->hTiles[t].glyph];
             size_t px = (size_t) d.w*(size_t) d.h-b->hTiles[t].pix0;
-            uint64_t cost = (uint64_t) (d.s1-d.s0)*(px < TILE_PIXELS ? px : (size_t) TILE_PIXELS);
-            keys[t] = (cost << 32)|(uint64_t) (0xffffffffu-(uint32_t) t);
+            size_t cost = (size_t) (d.s1-d.s0)*(px < TILE_PIXELS ? px : (size_t) TILE_PIXELS);      // <= SMEM_RECORDS*TILE_PIXELS
+            size_t c = cost*(CLASSES-1)/((size_t) SMEM_RECORDS*TILE_PIXELS);
+            cls[t] = (uint8_t) (CLASSES-1-(c < (size_t) CLASSES ? c : (size_t) CLASSES-1));         // class 0 = most expensive
+            ++count[cls[t]+1];
         }
-        std::sort(keys.begin(), keys.end(), std::greater<uint64_t>());
+        for (int c = 0; c < CLASSES; ++c)
+            count[c+1] += count[c];
         std::vector<TileDesc> sorted(n);
         for (size_t t = 0; t < n; ++t)
-            sorted[t] = b->hTiles[0xffffffffu-(uint32_t) (keys[t]&0xffffffffu)];
+            sorted[count[cls[t]]++] = b->hTiles[t];
         b->hTiles.swap(sorted);
     }
     b->nSmallTiles = (int) b->hTiles.size();
