@@ -15,6 +15,7 @@
 #include <new>
 #include <string>
 #include <algorithm>
+#include <chrono>
 #include <functional>
 #include <vector>
 
@@ -77,6 +78,17 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// B200MSDF_TRACE=1: host-side phase timing of the host-buffer entry points on stderr (microseconds since the call started)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("B200MSDF_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) { }
+    void mark(const char *what) const {
+        if (on)
+            fprintf(stderr, "[b200msdf] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now()-t0).count());
+    }
+};
+
 // exact-distance candidate slots per 1024-texel tile (the default configuration produces about 7; ALWAYS_CHECK_DISTANCE about 230)
 const int EC_CANDIDATES_PER_TILE = 384;
 
@@ -118,7 +130,8 @@ struct b200msdf_ctx {
     int numSMs = 0;
     cudaStream_t own = nullptr, stream = nullptr;
     cudaStream_t aux[2] = { nullptr, nullptr };     // double-buffered chunks of large host batches (copy/compute overlap)
-    PinBuf pinOut, pinIn;
+    PinBuf pinOut, pinIn, pinDesc;  // pinDesc: staging of per-batch descriptors (glyphs, tiles) so that their H2D copies are true async DMAs
+    cudaEvent_t descDone = nullptr; // the last copy out of pinDesc
     uint64_t launches = 0;
     b200msdf_batch pool;        // reused by the host-buffer entry points
     b200msdf_batch chunk[2];    // reused by the chunked host path
@@ -310,10 +323,28 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
         CUDA_TRY(cudaMemcpyAsync(b->cbegin.p, s->contour_segment_begin, (nCon+1)*4, cudaMemcpyHostToDevice, st));
     else
         CUDA_TRY(cudaMemsetAsync(b->cbegin.p, 0, 4, st));
-    if (!b->hGlyphs.empty())
-        CUDA_TRY(cudaMemcpyAsync(b->glyphs.p, b->hGlyphs.data(), sizeof(GlyphDesc)*b->hGlyphs.size(), cudaMemcpyHostToDevice, st));
-    if (!b->hTiles.empty())
-        CUDA_TRY(cudaMemcpyAsync(b->tiles.p, b->hTiles.data(), sizeof(TileDesc)*b->hTiles.size(), cudaMemcpyHostToDevice, st));
+    // glyph and tile descriptors go through pinned staging (a cudaMemcpyAsync from a pageable std::vector is staged and
+    // synchronous on the host)
+    {
+        const size_t gBytes = sizeof(GlyphDesc)*b->hGlyphs.size(), tBytes = sizeof(TileDesc)*b->hTiles.size();
+        if (gBytes+tBytes) {
+            if (ctx->descDone)
+                CUDA_TRY(cudaEventSynchronize(ctx->descDone));      // an earlier batch may still be reading the staging buffer
+            if ((rc = ctx->pinDesc.reserve(gBytes+tBytes+64))) return rc;
+            char *stage = static_cast<char *>(ctx->pinDesc.p);
+            if (gBytes) {
+                memcpy(stage, b->hGlyphs.data(), gBytes);
+                CUDA_TRY(cudaMemcpyAsync(b->glyphs.p, stage, gBytes, cudaMemcpyHostToDevice, st));
+            }
+            if (tBytes) {
+                memcpy(stage+gBytes, b->hTiles.data(), tBytes);
+                CUDA_TRY(cudaMemcpyAsync(b->tiles.p, stage+gBytes, tBytes, cudaMemcpyHostToDevice, st));
+            }
+            if (!ctx->descDone)
+                CUDA_TRY(cudaEventCreateWithFlags(&ctx->descDone, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(ctx->descDone, st));
+        }
+    }
     return 0;
 }
 
@@ -686,6 +717,8 @@ void b200msdf_destroy(b200msdf_ctx *ctx) {
     ctx->pool.release();
     ctx->pinOut.release();
     ctx->pinIn.release();
+    ctx->pinDesc.release();
+    if (ctx->descDone) cudaEventDestroy(ctx->descDone);
     if (ctx->own) cudaStreamDestroy(ctx->own);
     delete ctx;
 }
@@ -813,7 +846,9 @@ int b200msdf_generate_batch(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *
         return rc;
     }
     b200msdf_batch *b = &ctx->pool;
+    Trace trace;
     if ((rc = upload_batch(ctx, b, mode, shapes, xf, xfPerGlyph, dims.data(), 1, yd.data()))) return rc;
+    trace.mark("descriptors + H2D enqueued");
     // Zero-copy output: when the caller's sections form one packed block of pinned, device-accessible host memory (e.g. from
     // b200msdf_host_alloc), the kernels store the final texels straight into it over PCIe (coalesced float4 rows, posted
     // writes) while they are still computing, instead of a separate D2H copy after the last kernel.
@@ -829,9 +864,11 @@ int b200msdf_generate_batch(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *
     rc = launch_batch(ctx, b, config);
     b->outOverride = nullptr;
     if (rc) return rc;
+    trace.mark("kernels enqueued");
     if (!direct)
         if ((rc = download_to_bitmaps(ctx, b, b->out.as<float>(), outputs))) return rc;
     CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    trace.mark(direct ? "done (zero-copy output)" : "done (D2H copy)");
     return 0;
 }
 
