@@ -1,12 +1,15 @@
 // kernels.cuh — the sm_100a kernels of the hot path and their launch parameters.
 //
 //   k0_windings          one thread per contour: Contour::winding()  (/root/reference/core/Contour.cpp:57-81)
-//   k0_prepare_big       one thread per segment of shapes too large for shared memory: SegRec -> global buffer
+//   k0_prepare_big       one thread per segment of shapes too large for shared memory: SegRec (+ compact cull records) -> global
 //   k1_distance_field    generateDistanceField<Combiner<Selector>>    (/root/reference/core/msdfgen.cpp:52-76)
-//   k2_classify / k3_exact_distance   msdfErrorCorrectionInner<N> + apply  (error_correction.cuh)
+//   k1_big_blocks        the same for shapes with more than SMEM_RECORDS segments: 32x32 blocks, two-level record lists
+//   k2_classify / k3_exact_distance / k4_quantize   msdfErrorCorrectionInner<N> + apply, 8-bit output  (error_correction.cuh)
+//   k5_* (scanline.cuh) distanceSignCorrection / rasterize;  k6_* (render.cuh) renderSDF / simulate8bit
 //
 // Work decomposition: a tile is up to TILE_PIXELS consecutive output texels of one glyph; persistent CTAs of CTA_THREADS
-// threads pull tiles from an atomic counter (greedy list scheduling: glyph cost varies 8x with its segment count), stage
+// threads pull tiles from an atomic counter (greedy list scheduling, most expensive tiles first: glyph cost varies 8x with its
+// segment count), stage
 // the glyph's prepared segment records in shared memory once per tile, then every thread owns one texel per pass and walks
 // all records (broadcast shared-memory reads, no divergence on the segment type).  Texels are staged in shared memory and
 // written back as coalesced float4 rows.
