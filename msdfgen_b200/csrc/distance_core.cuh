@@ -64,7 +64,8 @@ __device__ __forceinline__ bool sd_less(double ad, double adot, double bd, doubl
 
 enum : int {
     SEG_LAST_IN_CONTOUR = 1,   // contour ends after this record (evaluation order)
-    SEG_CUBIC_NORMED = 2       // quadratic segment: foot-point cubic takes the normalised (trig/Cardano) branch
+    SEG_CUBIC_NORMED = 2,      // quadratic segment: foot-point cubic takes the normalised (trig/Cardano) branch
+    SEG_EXACT_ROOTS = 4        // quadratic segment with a cusp (vanishing tangent in [0,1]): literal closed-form roots, see sd_quadratic
 };
 
 // One prepared edge segment, in EVALUATION order (per contour: last edge first, then edges 0..n-2).
@@ -280,6 +281,14 @@ __device__ inline void prepare_record(const RawShapes &rs, const GlyphDesc &g, u
                 if (fabs(bn) < 1e6)
                     flags |= SEG_CUBIC_NORMED;
             }
+            // Cusps: control point on an end point, or collinear and doubling back.  The tangent vanishes at a parameter t* in
+            // [0,1] that is itself a root of the foot-point cubic, and what the reference returns for texels nearest to the
+            // cusp hinges on the last bits of that root (is it inside (0,1)? which sign has cross(~0, q)?).  The polished roots of
+            // the fast path are accurate but not bit-faithful, so these segments take the literal closed form, which follows
+            // the reference wherever its own outcome is not rounding noise.
+            d2 pq = P2-P1;
+            if (is_zero(ab) || is_zero(pq) || (cross(ab, pq) == 0 && dot(ab, pq) < 0))
+                flags |= SEG_EXACT_ROOTS;
         } else {
             d2 as = (P3-P2)-(P2-P1)-br;
             out.e[4] = as.x; out.e[5] = as.y;
@@ -500,8 +509,9 @@ __device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need
 #if B200_EXACT_ROOTS
         t = solve_cubic_normed(s.e[13], c/a, d/a);
 #else
-        bool ok;
-        t = solve_cubic_fast(s.e[13], c*s.p3.x, d*s.p3.x, ok);
+        bool ok = !(s.flags&SEG_EXACT_ROOTS);
+        if (ok)
+            t = solve_cubic_fast(s.e[13], c*s.p3.x, d*s.p3.x, ok);
         if (!ok)
             t = solve_cubic_normed(s.e[13], c/a, d/a);
 #endif
