@@ -33,6 +33,11 @@ namespace b200 {
 #define CLS_CANDIDATE 1
 #define CLS_ARTIFACT 2
 #define EC_WARPS (CTA_THREADS/32)
+// Experimental (off; not validated on hardware yet — see profiles/NOTES_r1.md): warp-level compaction of k2's out-of-line
+// artifact tests.  With 0 the code below is textually the round-1 kernel.
+#ifndef B200_K2_COMPACT
+#define B200_K2_COMPACT 0
+#endif
 
 // mix<float, double>(a, b, t)
 __device__ __forceinline__ float mixf(float a, float b, double t) { return float((1.0-t)*a+t*b); }
@@ -84,7 +89,22 @@ struct TexelState {
     d2 shapeCoord, sdfCoord;
     const float *msd;
     unsigned texel;
+#if B200_K2_COMPACT
+    // the neighbour walk only ENUMERATES the tests that survive the prefilters (owner lane, kind, neighbour, channel pair packed
+    // in 16 bits) into a per-warp queue; the warp then runs 32 queued tests at a time
+    unsigned short *queue;
+    int *queueCount;
+    int lane;
+#endif
 };
+
+#if B200_K2_COMPACT
+#define K2_QUEUE (32*24)        // at most 8 neighbours x 3 channel pairs per texel
+__device__ __forceinline__ void enqueue_test(TexelState &k, int kind, int n, int pr) {
+    int at = atomicAdd(k.queueCount, 1);
+    k.queue[at] = (unsigned short) (k.lane|(kind<<5)|(n<<6)|(pr<<8));
+}
+#endif
 
 // BaseArtifactClassifier::rangeTest (:30-41)
 __device__ __forceinline__ int range_test(bool protectedFlag, double span, double at, double bt, double xt, float am, float bm, float xm) {
@@ -273,6 +293,9 @@ __device__ __forceinline__ void find_errors_texel(const EcCtx<N> &e, TexelState 
             // is skipped without changing a result.
             float dA = a1-a0, dB = b1-b0;
             if ((dA > 0 && dB < 0) || (dA < 0 && dB > 0))
+#if B200_K2_COMPACT
+                if (SINK == 0) enqueue_test(k, 0, n, pr); else
+#endif
                 linear_artifact_inner<N, SINK, OVERLAP>(e, k, am, bm, a, b, dA, dB);
         }
     }
@@ -319,10 +342,62 @@ __device__ __forceinline__ void find_errors_texel(const EcCtx<N> &e, TexelState 
             // inside), and a non-negative discriminant (the very expression solveQuadratic evaluates)
             const bool vertexInside = (qa > 0 && qb < 0 && -qb < 2*qa && qc >= 0) || (qa < 0 && qb > 0 && qb < -2*qa && qc <= 0);
             if (signChange || (vertexInside && qb*qb-4*qa*qc >= 0))
+#if B200_K2_COMPACT
+                if (SINK == 0) enqueue_test(k, 1, n, pr); else
+#endif
                 diagonal_artifact_inner<N, SINK, OVERLAP>(e, k, am, dm, a, l, q, dA, dBC, dD, i0, i1, extremes);
         }
     }
 }
+
+#if B200_K2_COMPACT
+// One queued test (B200_K2_COMPACT): rebuilds exactly the operands find_errors_texel had at the enqueue site for texel
+// (x, y), neighbour n and channel pair pr, and runs the out-of-line test.  k carries the owner's protection flags in and the
+// verdict bits out.
+template <int N>
+__device__ __forceinline__ void run_queued_test(const EcCtx<N> &e, TexelState &k, int x, int y, int kind, int n, int pr, double hSpan, double vSpan, double dSpan) {
+    const float *c = e.f.at(x, y);
+    const float a[3] = { c[0], c[1], c[2] };
+    const float am = median3f(a[0], a[1], a[2]);
+    k.sdfCoord = mk(x+.5, y+.5);
+    k.shapeCoord = mk((x+.5)/e.g->sx-e.g->tx, (y+.5)/e.g->sy-e.g->ty);
+    k.msd = c;
+    #define B200_PICK(v, i) ((i) == 0 ? v[0] : (i) == 1 ? v[1] : v[2])
+    if (kind == 0) {
+        const int dx = n == 0 ? -1 : n == 2 ? 1 : 0;
+        const int dy = n == 1 ? -1 : n == 3 ? 1 : 0;
+        const float *bp = e.f.at(x+dx, y+dy);
+        const float b[3] = { bp[0], bp[1], bp[2] };
+        const float bm = median3f(b[0], b[1], b[2]);
+        k.direction = mk(dx, dy);
+        k.span = dx ? hSpan : vSpan;
+        const int i0 = pr, i1 = pr == 2 ? 0 : pr+1;
+        const float dA = B200_PICK(a, i1)-B200_PICK(a, i0), dB = B200_PICK(b, i1)-B200_PICK(b, i0);
+        linear_artifact_inner<N, 0, false>(e, k, am, bm, a, b, dA, dB);
+    } else {
+        const int dx = (n&1) ? 1 : -1;
+        const int dy = (n&2) ? 1 : -1;
+        const float *dp = e.f.at(x+dx, y+dy), *bp = e.f.at(x+dx, y), *cp = e.f.at(x, y+dy);
+        const float d[3] = { dp[0], dp[1], dp[2] };
+        const float b[3] = { bp[0], bp[1], bp[2] };
+        const float cc[3] = { cp[0], cp[1], cp[2] };
+        const float dm = median3f(d[0], d[1], d[2]);
+        k.direction = mk(dx, dy);
+        k.span = dSpan;
+        float abc[3] = { a[0]-b[0]-cc[0], a[1]-b[1]-cc[1], a[2]-b[2]-cc[2] };
+        float l[3] = { -a[0]-abc[0], -a[1]-abc[1], -a[2]-abc[2] };
+        float q[3] = { d[0]+abc[0], d[1]+abc[1], d[2]+abc[2] };
+        const int i0 = pr, i1 = pr == 2 ? 0 : pr+1;
+        const float a0 = B200_PICK(a, i0), a1 = B200_PICK(a, i1), b0 = B200_PICK(b, i0), b1 = B200_PICK(b, i1);
+        const float c0 = B200_PICK(cc, i0), c1 = B200_PICK(cc, i1), d0 = B200_PICK(d, i0), d1 = B200_PICK(d, i1);
+        const float dA = a1-a0, dBC = b1-b0+c1-c0, dD = d1-d0;
+        DiagonalExtremes extremes;
+        extremes.have = 0;
+        diagonal_artifact_inner<N, 0, false>(e, k, am, dm, a, l, q, dA, dBC, dD, i0, i1, extremes);
+    }
+    #undef B200_PICK
+}
+#endif
 
 // edgeBetweenTexelsChannel (:154-169)
 __device__ __forceinline__ bool edge_between_channel(float a0, float a1, float a2, float b0, float b1, float b2, int ch) {
@@ -433,6 +508,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
     __shared__ GlyphDesc s_g;
     __shared__ int s_tile;
     __shared__ int s_chunk;
+#if B200_K2_COMPACT
+    __shared__ unsigned short s_queue[EC_WARPS][K2_QUEUE];
+    __shared__ int s_queueCount[EC_WARPS];
+    __shared__ int s_verdict[EC_WARPS][32];      // per owner lane: bit 0 protBase, 1 protShape (in); 2 errBase, 3 errShape, 4 overflow (out)
+#endif
 
     const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
     int stagedGlyph = -1;
@@ -496,6 +576,106 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
                 blockOrigin = td.pix0+by*4u*unsigned(w)+bx*8u;
                 i = blockOrigin+unsigned(lane>>3)*unsigned(w)+unsigned(lane&7);
             }
+#if B200_K2_COMPACT
+            if (lane == 0)
+                s_queueCount[warp] = 0;
+            __syncwarp();
+            int x = 0, y = 0, flags = 0;
+            TexelState k;
+            if (i < tileEnd) {
+                x = int(i%unsigned(w));
+                int yOut = int(i/unsigned(w));
+                y = s_g.flip ? h-1-yOut : yOut;
+                // msdfErrorCorrectionInner: protection stage
+                if (P.ecMode == 2) {
+                    bool prot = false;
+                    if (needCorners)
+                        for (int j = 0; j < nRec; ++j) {
+                            int cl, cb;
+                            if (bigRecs) { cl = bigRecs[j].cornerL; cb = bigRecs[j].cornerB; }
+                            else { int2 c = s_corner[j]; cl = c.x; cb = c.y; }
+                            if (unsigned(x-cl) <= 1u && unsigned(y-cb) <= 1u)
+                                prot = true;
+                        }
+                    if (!prot)
+                        prot = protect_edges_texel<N>(e.f, x, y, sp.hRadius, sp.vRadius, sp.dRadius);
+                    if (prot)
+                        flags |= EC_FLAG_PROTECTED;
+                } else if (P.ecMode == 3)
+                    flags |= EC_FLAG_PROTECTED;
+                // detection stage: both passes in one walk
+                k.useBase = useBase;
+                k.protBase = (flags&EC_FLAG_PROTECTED) != 0;
+                k.useShape = useShape;
+                // protectAll() runs between the two passes when distanceCheckMode == CHECK_DISTANCE_AT_EDGE
+                k.protShape = k.protBase || (useBase && P.ecDcm == 1);
+                k.errBase = k.errShape = k.overflow = false;
+                k.texel = i;
+                k.queue = s_queue[warp];
+                k.queueCount = &s_queueCount[warp];
+                k.lane = lane;
+                s_verdict[warp][lane] = (k.protBase ? 1 : 0)|(k.protShape ? 2 : 0);
+                find_errors_texel<N, 0, false>(e, k, x, y, sp.hSpan, sp.vSpan, sp.dSpan);     // SINK 0: enumerates
+            }
+            __syncwarp();
+            // the warp runs the queued tests 32 at a time; verdicts go back to the owners through shared memory
+            {
+                const int nQueued = s_queueCount[warp];
+                for (int base = 0; base < nQueued; base += 32) {
+                    const int q = base+lane;
+                    if (q < nQueued) {
+                        const unsigned item = s_queue[warp][q];
+                        const int owner = int(item&31u), kind = int((item>>5)&1u), n = int((item>>6)&3u), pr = int((item>>8)&3u);
+                        const unsigned io = blocked ? blockOrigin+unsigned(owner>>3)*unsigned(w)+unsigned(owner&7) : chunkBase+unsigned(owner);
+                        const int ox = int(io%unsigned(w));
+                        const int oyOut = int(io/unsigned(w));
+                        const int oy = s_g.flip ? h-1-oyOut : oyOut;
+                        const int state = *(volatile int *) &s_verdict[warp][owner];
+                        TexelState t;
+                        t.useBase = useBase; t.useShape = useShape;
+                        t.protBase = (state&1) != 0; t.protShape = (state&2) != 0;
+                        // an owner already found in error needs no exact-distance candidates (classify_point's short cut)
+                        const bool knownError = (state&12) != 0;
+                        t.errBase = knownError; t.errShape = false; t.overflow = false;
+                        t.texel = io;
+                        t.queue = nullptr; t.queueCount = nullptr; t.lane = owner;
+                        run_queued_test<N>(e, t, ox, oy, kind, n, pr, sp.hSpan, sp.vSpan, sp.dSpan);
+                        const int bits = ((t.errBase && !knownError) ? 4 : 0)|(t.errShape ? 8 : 0)|(t.overflow ? 16 : 0);
+                        if (bits)
+                            atomicOr(&s_verdict[warp][owner], bits);
+                    }
+                }
+            }
+            __syncwarp();
+            if (i < tileEnd) {
+                {
+                    const int state = s_verdict[warp][lane];
+                    k.errBase = (state&4) != 0;
+                    k.errShape = (state&8) != 0;
+                    k.overflow = (state&16) != 0;
+                }
+                if (k.errBase || k.errShape)
+                    flags |= EC_FLAG_ERROR;
+                if (k.protShape && useShape)
+                    flags |= EC_FLAG_PROTECTED;
+                if (k.overflow && !(flags&EC_FLAG_ERROR))
+                    flags |= EC_FLAG_RECHECK;
+                // apply (:459-479)
+                const float *c = e.f.at(x, y);
+                float o0 = c[0], o1 = c[1], o2 = c[2];
+                if (flags&EC_FLAG_ERROR) {
+                    float m = median3f(o0, o1, o2);
+                    o0 = m; o1 = m; o2 = m;
+                }
+                s_out[warp][lane*N+0] = o0;
+                s_out[warp][lane*N+1] = o1;
+                s_out[warp][lane*N+2] = o2;
+                if (N == 4)
+                    s_out[warp][lane*N+3] = c[3];
+                int srow = s_g.shapeYDown ? h-1-y : y;
+                P.stencil[s_g.texelOffset+size_t(srow)*w+x] = (uint8_t) flags;
+            }
+#else
             if (i < tileEnd) {
                 int x = int(i%unsigned(w));
                 int yOut = int(i/unsigned(w));
@@ -549,6 +729,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
                 int srow = s_g.shapeYDown ? h-1-y : y;
                 P.stencil[s_g.texelOffset+size_t(srow)*w+x] = (uint8_t) flags;
             }
+#endif
             __syncwarp();
             // coalesced write-back of the chunk (float4 when aligned)
             if (blocked) {
