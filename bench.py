@@ -15,6 +15,7 @@ A step = one pass of the hot path (contour windings -> distance field -> error c
 The oracle (oracle/) is used only by the cpu_baseline leg and by --impl reference, as the thing timed on the CPU.
 """
 import argparse
+import atexit
 import json
 import os
 import subprocess
@@ -56,12 +57,17 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            atexit.register(self._kill)         # never leave the sampler behind, whatever happens to the run
         except Exception:
             self.proc = None
+
+    def _kill(self):
+        if self.proc and self.proc.poll() is None:
+            self.proc.kill()
 
     def _read(self):
         for line in self.proc.stdout:
@@ -72,18 +78,22 @@ class ClockSampler:
             return None
         time.sleep(0.15)
         self.proc.terminate()
+        # samples inside the timed region; the region is ~0.1 s, so if the 50 ms sampling grid missed it take the samples within
+        # 0.25 s around it (the GPU is under the same load during warm-up and the stage timing that follow immediately)
+        inside = [t for t, _ in self.rows if t0 - 0.05 <= t <= t1 + 0.05]
+        pad = 0.05 if inside else 0.25
         sm, mx, reasons = [], [], set()
         for t, line in self.rows:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                if t0 - 0.05 <= t <= t1 + 0.05:
+                if t0 - pad <= t <= t1 + pad:
                     sm.append(float(f[0]))
                 mx.append(float(f[1]))
             except ValueError:
                 continue
-            if t0 - 0.05 <= t <= t1 + 0.05:
+            if t0 - pad <= t <= t1 + pad:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
@@ -203,6 +213,9 @@ def main():
 
     mode = {"sdf": api.SDF, "psdf": api.PSDF, "msdf": api.MSDF, "mtsdf": api.MTSDF}[args.mode]
     channels = api.CHANNELS[mode]
+    # nvidia-smi takes a few hundred ms to start streaming: launch it before the host-side workload preparation (seconds), so
+    # that it is sampling every 50 ms by the time the ~0.1 s timed region runs
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     atlas, xf = workload(args.glyphs, args.size, rank)
     px_rank = atlas.n_glyphs * args.size * args.size
     cfg = api.MSDFGeneratorConfig()
@@ -225,7 +238,6 @@ def main():
     for _ in range(args.warmup):
         step_events()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ctx.launch_count
     t_wall0 = time.perf_counter()
     evs = [step_events() for _ in range(args.steps)]
