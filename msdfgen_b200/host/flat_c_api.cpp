@@ -5,7 +5,9 @@
 #include "msdfgen.h"
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 using namespace msdfgen;
@@ -29,6 +31,33 @@ void buildShape(Shape &shape, const uint32_t *cbegin, uint32_t c0, uint32_t c1, 
     }
 }
 
+// Glyphs are independent, so the batch entry points split [0, n) into contiguous ranges over host threads (the GPU needs
+// ~1.2 us per glyph; preparation costs ~5 us per glyph of CPU time plus as much again in allocator work, which would make it
+// the slowest stage of an atlas build).  At most 16 threads by default; B200MSDF_HOST_THREADS overrides the count.  Measured in
+// the 8-vCPU build container on 4096 glyphs: prepare 22 -> 5 ms, flatten 3 -> 1 ms, teardown 8 -> 5 ms with a warm heap; with a
+// cold heap (fresh output arrays every call) the page faults of the allocator dominate and the split gains nothing.
+template <typename F>
+void parallelRanges(size_t n, size_t grain, F body) {
+    size_t threads = std::thread::hardware_concurrency();
+    if (threads > 16)
+        threads = 16;
+    if (const char *env = std::getenv("B200MSDF_HOST_THREADS"))
+        threads = (size_t) std::atoi(env);
+    if (threads > n/grain)
+        threads = n/grain;
+    if (threads <= 1) {
+        body(size_t(0), n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve(threads-1);
+    for (size_t t = 1; t < threads; ++t)
+        pool.emplace_back(body, n*t/threads, n*(t+1)/threads);
+    body(size_t(0), n/threads);
+    for (size_t t = 0; t < pool.size(); ++t)
+        pool[t].join();
+}
+
 }  // namespace
 
 extern "C" {
@@ -44,18 +73,22 @@ int b200host_prepare_begin(int nGlyphs, const uint32_t *gbegin, const uint32_t *
                            b200host_prepared **handle, int *outContours, int *outSegments) {
     b200host_prepared *h = new b200host_prepared;
     h->shapes.resize((size_t) nGlyphs);
+    parallelRanges((size_t) nGlyphs, 64, [&](size_t g0, size_t g1) {
+        for (size_t g = g0; g < g1; ++g) {
+            Shape &shape = h->shapes[g];
+            buildShape(shape, cbegin, gbegin[g], gbegin[g+1], points, orders, colors, yDown ? yDown[g] != 0 : false);
+            if (doNormalize)
+                shape.normalize();
+            if (coloring == 1)
+                edgeColoringSimple(shape, angleThreshold, seed);
+            else if (coloring == 2)
+                edgeColoringInkTrap(shape, angleThreshold, seed);
+        }
+    });
     int nc = 0, ns = 0;
     for (int g = 0; g < nGlyphs; ++g) {
-        Shape &shape = h->shapes[(size_t) g];
-        buildShape(shape, cbegin, gbegin[g], gbegin[g+1], points, orders, colors, yDown ? yDown[g] != 0 : false);
-        if (doNormalize)
-            shape.normalize();
-        if (coloring == 1)
-            edgeColoringSimple(shape, angleThreshold, seed);
-        else if (coloring == 2)
-            edgeColoringInkTrap(shape, angleThreshold, seed);
-        nc += (int) shape.contours.size();
-        ns += shape.edgeCount();
+        nc += (int) h->shapes[(size_t) g].contours.size();
+        ns += h->shapes[(size_t) g].edgeCount();
     }
     *handle = h;
     *outContours = nc;
@@ -64,10 +97,18 @@ int b200host_prepare_begin(int nGlyphs, const uint32_t *gbegin, const uint32_t *
 }
 
 int b200host_prepare_fetch(b200host_prepared *h, uint32_t *gbegin, uint32_t *cbegin, double *points, uint8_t *orders, uint8_t *colors) {
-    uint32_t c = 0, s = 0;
+    // offsets first (serial, O(glyphs)), then every thread flattens its own glyph range
+    const size_t n = h->shapes.size();
+    std::vector<uint32_t> segBegin(n+1, 0);
     gbegin[0] = 0;
     cbegin[0] = 0;
-    for (size_t g = 0; g < h->shapes.size(); ++g) {
+    for (size_t g = 0; g < n; ++g) {
+        gbegin[g+1] = gbegin[g]+(uint32_t) h->shapes[g].contours.size();
+        segBegin[g+1] = segBegin[g]+(uint32_t) h->shapes[g].edgeCount();
+    }
+    parallelRanges(n, 64, [&](size_t g0, size_t g1) {
+    for (size_t g = g0; g < g1; ++g) {
+        uint32_t c = gbegin[g], s = segBegin[g];
         const Shape &shape = h->shapes[g];
         for (size_t ci = 0; ci < shape.contours.size(); ++ci) {
             const std::vector<EdgeHolder> &edges = shape.contours[ci].edges;
@@ -85,12 +126,21 @@ int b200host_prepare_fetch(b200host_prepared *h, uint32_t *gbegin, uint32_t *cbe
             }
             cbegin[++c] = s;
         }
-        gbegin[g+1] = c;
     }
+    });
     return 0;
 }
 
-void b200host_prepare_free(b200host_prepared *h) { delete h; }
+void b200host_prepare_free(b200host_prepared *h) {
+    if (!h)
+        return;
+    // tearing down ~36 heap-allocated segments per glyph is as expensive as building them: same split over threads
+    parallelRanges(h->shapes.size(), 64, [&](size_t g0, size_t g1) {
+        for (size_t g = g0; g < g1; ++g)
+            std::vector<Contour>().swap(h->shapes[g].contours);
+    });
+    delete h;
+}
 
 /// Contour::winding() of every contour; Shape::validate() and Shape::getBounds() per glyph.
 int b200host_windings(int nContours, const uint32_t *cbegin, const double *points, const uint8_t *orders, int *out) {

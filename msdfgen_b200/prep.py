@@ -48,9 +48,12 @@ def prepare(shapes: FlatShapes, normalize=True, coloring="simple", angle_thresho
     try:
         gb = np.zeros(shapes.n_glyphs + 1, np.uint32)
         cb = np.zeros(nc.value + 1, np.uint32)
-        pts = np.zeros((ns.value, 8), np.float64)
-        od = np.zeros(ns.value, np.uint8)
-        cl = np.zeros(ns.value, np.uint8)
+        # b200host_prepare_fetch writes every element; touching the pages here (one thread) keeps the worker threads of the
+        # fetch from serialising on first-touch page faults
+        pts = np.empty((ns.value, 8), np.float64)
+        pts.fill(0.0)
+        od = np.empty(ns.value, np.uint8)
+        cl = np.empty(ns.value, np.uint8)
         lib.b200host_prepare_fetch(h, _p(gb, C.c_uint32), _p(cb, C.c_uint32), _p(pts, C.c_double), _p(od, C.c_uint8), _p(cl, C.c_uint8))
     finally:
         lib.b200host_prepare_free(h)
