@@ -3,6 +3,7 @@
 // colouring on every glyph, and flattens the result again.  Host-only (no device work); this is the batch-ingest step that
 // precedes b200msdf_generate_batch (SURVEY.md §8f "next" #1).
 #include "msdfgen.h"
+#include "flat_prep.h"
 
 #include <cstdint>
 #include <cstdlib>
@@ -65,7 +66,13 @@ extern "C" {
 /// Pass 1 of 2: prepares every glyph and returns the totals needed to size the output arrays. The prepared shapes are kept
 /// in an opaque handle until b200host_prepare_fetch / b200host_prepare_free.
 struct b200host_prepared {
-    std::vector<Shape> shapes;
+    std::vector<Shape> shapes;          // glyphs that went through the general path (empty Shape for the others)
+    std::vector<uint8_t> flat;          // 1: the glyph's geometry is unchanged, only colours were computed (flatColors)
+    std::vector<uint8_t> flatColors;    // per input segment
+    // the caller's input arrays: flat glyphs are copied from them by b200host_prepare_fetch, so they must stay alive until then
+    const uint32_t *gbegin, *cbegin;
+    const double *points;
+    const uint8_t *orders;
 };
 
 int b200host_prepare_begin(int nGlyphs, const uint32_t *gbegin, const uint32_t *cbegin, const double *points, const uint8_t *orders, const uint8_t *colors,
@@ -73,8 +80,19 @@ int b200host_prepare_begin(int nGlyphs, const uint32_t *gbegin, const uint32_t *
                            b200host_prepared **handle, int *outContours, int *outSegments) {
     b200host_prepared *h = new b200host_prepared;
     h->shapes.resize((size_t) nGlyphs);
+    h->flat.assign((size_t) nGlyphs, 0);
+    h->flatColors.resize(nGlyphs > 0 ? (size_t) cbegin[gbegin[nGlyphs]] : 0);
+    h->gbegin = gbegin; h->cbegin = cbegin; h->points = points; h->orders = orders;
+    // B200MSDF_HOST_FLAT=0 forces every glyph through the Shape objects (for testing the two paths against each other)
+    const char *flatEnv = std::getenv("B200MSDF_HOST_FLAT");
+    const bool tryFlat = !(flatEnv && flatEnv[0] == '0');
     parallelRanges((size_t) nGlyphs, 64, [&](size_t g0, size_t g1) {
         for (size_t g = g0; g < g1; ++g) {
+            // almost every glyph keeps its geometry: colours are then computed straight from the flat arrays, no allocation
+            if (tryFlat && b200::prepareGlyphFlat(cbegin, gbegin[g], gbegin[g+1], points, orders, colors, doNormalize != 0, coloring, angleThreshold, seed, h->flatColors.data())) {
+                h->flat[g] = 1;
+                continue;
+            }
             Shape &shape = h->shapes[g];
             buildShape(shape, cbegin, gbegin[g], gbegin[g+1], points, orders, colors, yDown ? yDown[g] != 0 : false);
             if (doNormalize)
@@ -87,8 +105,13 @@ int b200host_prepare_begin(int nGlyphs, const uint32_t *gbegin, const uint32_t *
     });
     int nc = 0, ns = 0;
     for (int g = 0; g < nGlyphs; ++g) {
-        nc += (int) h->shapes[(size_t) g].contours.size();
-        ns += h->shapes[(size_t) g].edgeCount();
+        if (h->flat[(size_t) g]) {
+            nc += (int) (gbegin[g+1]-gbegin[g]);
+            ns += (int) (cbegin[gbegin[g+1]]-cbegin[gbegin[g]]);
+        } else {
+            nc += (int) h->shapes[(size_t) g].contours.size();
+            ns += h->shapes[(size_t) g].edgeCount();
+        }
     }
     *handle = h;
     *outContours = nc;
@@ -103,12 +126,32 @@ int b200host_prepare_fetch(b200host_prepared *h, uint32_t *gbegin, uint32_t *cbe
     gbegin[0] = 0;
     cbegin[0] = 0;
     for (size_t g = 0; g < n; ++g) {
-        gbegin[g+1] = gbegin[g]+(uint32_t) h->shapes[g].contours.size();
-        segBegin[g+1] = segBegin[g]+(uint32_t) h->shapes[g].edgeCount();
+        if (h->flat[g]) {
+            gbegin[g+1] = gbegin[g]+(h->gbegin[g+1]-h->gbegin[g]);
+            segBegin[g+1] = segBegin[g]+(h->cbegin[h->gbegin[g+1]]-h->cbegin[h->gbegin[g]]);
+        } else {
+            gbegin[g+1] = gbegin[g]+(uint32_t) h->shapes[g].contours.size();
+            segBegin[g+1] = segBegin[g]+(uint32_t) h->shapes[g].edgeCount();
+        }
     }
     parallelRanges(n, 64, [&](size_t g0, size_t g1) {
     for (size_t g = g0; g < g1; ++g) {
         uint32_t c = gbegin[g], s = segBegin[g];
+        if (h->flat[g]) {
+            // unchanged geometry: block copy of the input segments (unused control-point slots zeroed like the general path)
+            const uint32_t ic0 = h->gbegin[g], ic1 = h->gbegin[g+1];
+            const uint32_t is0 = h->cbegin[ic0], is1 = h->cbegin[ic1];
+            for (uint32_t ic = ic0; ic < ic1; ++ic)
+                cbegin[++c] = s+(h->cbegin[ic+1]-is0);
+            for (uint32_t is = is0; is < is1; ++is, ++s) {
+                const int order = h->orders[is];
+                for (int k = 0; k < 8; ++k)
+                    points[8*size_t(s)+k] = k < 2*(order+1) ? h->points[8*size_t(is)+k] : 0;
+                orders[s] = h->orders[is];
+                colors[s] = h->flatColors[is];
+            }
+            continue;
+        }
         const Shape &shape = h->shapes[g];
         for (size_t ci = 0; ci < shape.contours.size(); ++ci) {
             const std::vector<EdgeHolder> &edges = shape.contours[ci].edges;

@@ -8,6 +8,7 @@
 //   edge-segments.cpp:10-26,54-139,405-531   EdgeHolder.cpp   Contour.cpp   Shape.cpp:29-115,190-206
 //   convergent-curve-ordering.cpp   edge-coloring.cpp:19-258   equation-solver.cpp:9-32 (for cubic bounds)
 #include "msdfgen.h"
+#include "flat_prep.h"
 
 #include <cstdlib>
 
@@ -739,6 +740,179 @@ void edgeColoringInkTrap(Shape &shape, double angleThreshold, unsigned long long
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Allocation-free preparation of one glyph on flat arrays (flat_prep.h).  Segments are materialised as STACK objects of the
+// same classes the Shape path uses, so every direction / point / length is computed by the very same member functions; the
+// colouring logic below is the one above with `contour.edges[i]->color = c` replaced by `outColors[first+i] = c`.
+
+namespace b200 {
+
+namespace {
+
+// A segment of any order living on the stack (no heap, no clone)
+struct StackEdge {
+    int order;
+    Point2 p[4];
+    StackEdge(const double *q, int o) : order(o) {
+        for (int k = 0; k < 4; ++k)
+            p[k] = Point2(q[2*k], q[2*k+1]);
+    }
+    Vector2 direction(double t) const {
+        switch (order) {
+            case 1: return LinearSegment(p[0], p[1]).direction(t);
+            case 2: return QuadraticSegment(p[0], p[1], p[2]).direction(t);
+            default: return CubicSegment(p[0], p[1], p[2], p[3]).direction(t);
+        }
+    }
+    double polylineLength() const {
+        switch (order) {
+            case 1: { LinearSegment e(p[0], p[1]); return msdfgen::polylineLength(&e); }
+            case 2: { QuadraticSegment e(p[0], p[1], p[2]); return msdfgen::polylineLength(&e); }
+            default: { CubicSegment e(p[0], p[1], p[2], p[3]); return msdfgen::polylineLength(&e); }
+        }
+    }
+};
+
+}  // namespace
+
+bool prepareGlyphFlat(const uint32_t *cbegin, uint32_t c0, uint32_t c1, const double *points, const uint8_t *orders, const uint8_t *inColors,
+                      bool doNormalize, int coloring, double angleThreshold, unsigned long long seed, uint8_t *outColors) {
+    const double cuspDot = MSDFGEN_CORNER_DOT_EPSILON-1;
+    const double crossThreshold = std::sin(angleThreshold);
+    // ---- pass 1: does anything change the geometry?  (Shape::normalize, paintTeardrop's split)
+    // The unit tangents at both ends of every edge are kept for pass 2 (they are the bulk of the arithmetic).
+    static thread_local std::vector<Vector2> tangents;      // [2*k] = direction(0).normalize(), [2*k+1] = direction(1).normalize()
+    const uint32_t s0 = cbegin[c0];
+    tangents.resize(2*size_t(cbegin[c1]-s0));
+    for (uint32_t s = s0; s < cbegin[c1]; ++s) {
+        const StackEdge edge(points+8*size_t(s), orders[s]);
+        tangents[2*size_t(s-s0)] = edge.direction(0).normalize();
+        tangents[2*size_t(s-s0)+1] = edge.direction(1).normalize();
+    }
+    for (uint32_t c = c0; c < c1; ++c) {
+        const uint32_t first = cbegin[c], n = cbegin[c+1]-first;
+        if (n == 0)
+            continue;
+        if (doNormalize && n == 1)
+            return false;                                   // single-edge contour: split in thirds
+        int cornerCount = 0;
+        Vector2 inDir = tangents[2*size_t(first+n-1-s0)+1];
+        for (uint32_t i = 0; i < n; ++i) {
+            const Vector2 outDir = tangents[2*size_t(first+i-s0)];
+            if (doNormalize && n > 1 && dotProduct(inDir, outDir) < cuspDot)
+                return false;                               // cusp: control points get pushed apart
+            if (coloring && sharpCorner(inDir, outDir, crossThreshold))
+                ++cornerCount;
+            inDir = tangents[2*size_t(first+i-s0)+1];
+        }
+        if (coloring && cornerCount == 1 && n < 3)
+            return false;                                   // teardrop of one or two edges: split to make room for three colours
+    }
+    // ---- pass 2: colours
+    if (!coloring) {
+        for (uint32_t s = cbegin[c0]; s < cbegin[c1]; ++s)
+            outColors[s] = inColors ? inColors[s] : (uint8_t) WHITE;
+        return true;
+    }
+    struct Corner {
+        int index;
+        double precedingLength;
+        bool minor;
+        EdgeColor color;
+    };
+    static thread_local std::vector<Corner> corners;
+    ColorStream stream(seed);
+    for (uint32_t c = c0; c < c1; ++c) {
+        const uint32_t first = cbegin[c];
+        const int m = int(cbegin[c+1]-first);
+        if (m == 0)
+            continue;
+        uint8_t *colors = outColors+first;
+        double splineLength = 0;
+        corners.clear();
+        Vector2 inDir = tangents[2*size_t(first+m-1-s0)+1];
+        for (int i = 0; i < m; ++i) {
+            if (sharpCorner(inDir, tangents[2*size_t(first+i-s0)], crossThreshold)) {
+                Corner corner = { i, splineLength, false, BLACK };
+                corners.push_back(corner);
+                splineLength = 0;
+            }
+            if (coloring == 2)
+                splineLength += StackEdge(points+8*size_t(first+i), orders[first+i]).polylineLength();
+            inDir = tangents[2*size_t(first+i-s0)+1];
+        }
+        const int cornerCount = (int) corners.size();
+        if (cornerCount == 0) {                 // paintSmoothContour
+            stream.advance();
+            for (int i = 0; i < m; ++i)
+                colors[i] = (uint8_t) stream.color;
+        } else if (cornerCount == 1) {          // paintTeardrop, m >= 3
+            EdgeColor three[3];
+            stream.advance();
+            three[0] = stream.color;
+            three[1] = WHITE;
+            stream.advance();
+            three[2] = stream.color;
+            for (int i = 0; i < m; ++i)
+                colors[(corners[0].index+i)%m] = (uint8_t) three[1+thirdOf(i, m)];
+        } else if (coloring == 1) {             // edgeColoringSimple
+            int spline = 0;
+            const int start = corners[0].index;
+            stream.advance();
+            const EdgeColor initialColor = stream.color;
+            for (int i = 0; i < m; ++i) {
+                const int index = (start+i)%m;
+                if (spline+1 < cornerCount && corners[spline+1].index == index) {
+                    ++spline;
+                    stream.advance(EdgeColor((spline == cornerCount-1)*initialColor));
+                }
+                colors[index] = (uint8_t) stream.color;
+            }
+        } else {                                // edgeColoringInkTrap
+            int majorCornerCount = cornerCount;
+            if (cornerCount > 3) {
+                corners[0].precedingLength += splineLength;
+                for (int i = 0; i < cornerCount; ++i) {
+                    if (corners[i].precedingLength > corners[(i+1)%cornerCount].precedingLength &&
+                        corners[(i+1)%cornerCount].precedingLength < corners[(i+2)%cornerCount].precedingLength) {
+                        corners[i].minor = true;
+                        --majorCornerCount;
+                    }
+                }
+            }
+            EdgeColor initialColor = BLACK;
+            for (int i = 0; i < cornerCount; ++i) {
+                if (!corners[i].minor) {
+                    --majorCornerCount;
+                    stream.advance(EdgeColor(!majorCornerCount*initialColor));
+                    corners[i].color = stream.color;
+                    if (!initialColor)
+                        initialColor = stream.color;
+                }
+            }
+            for (int i = 0; i < cornerCount; ++i) {
+                if (corners[i].minor) {
+                    EdgeColor nextColor = corners[(i+1)%cornerCount].color;
+                    corners[i].color = EdgeColor((stream.color&nextColor)^WHITE);
+                } else
+                    stream.color = corners[i].color;
+            }
+            int spline = 0;
+            const int start = corners[0].index;
+            stream.color = corners[0].color;
+            for (int i = 0; i < m; ++i) {
+                const int index = (start+i)%m;
+                if (spline+1 < cornerCount && corners[spline+1].index == index)
+                    stream.color = corners[++spline].color;
+                colors[index] = (uint8_t) stream.color;
+            }
+        }
+    }
+    return true;
+}
+
+}  // namespace b200
 
 const double ErrorCorrectionConfig::defaultMinDeviationRatio = 1.11111111111111111;
 const double ErrorCorrectionConfig::defaultMinImproveRatio = 1.11111111111111111;

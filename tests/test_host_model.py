@@ -86,3 +86,33 @@ def test_bounds():
     assert l <= ends[:, 0].min() + 1e-12 and r >= ends[:, 0].max() - 1e-12 and b <= ends[:, 1].min() + 1e-12 and t >= ends[:, 1].max() - 1e-12
     lb, bb, rb, tb = prep.bounds(s, border=0.1)
     assert lb <= l - 0.1 + 1e-12 and rb >= r + 0.1 - 1e-12
+
+
+def test_flat_preparation_path_equals_shape_path():
+    """libmsdfgen_b200_host prepares glyphs whose geometry the preparation leaves untouched straight from the flat arrays
+    (host/flat_prep.h: no Shape objects, no allocation) and falls back to the Shape member functions for the rest (single-edge
+    contours, cusps, tiny teardrops).  Both paths must produce identical batches; B200MSDF_HOST_FLAT=0 disables the fast one."""
+    import os
+    from util import fuzz_shape
+    from msdfgen_b200.flat import FlatShapes
+    from msdfgen_b200.synth import synth_atlas
+
+    def both(shapes, **kw):
+        os.environ["B200MSDF_HOST_FLAT"] = "0"
+        try:
+            general = prep.prepare(shapes, **kw)
+        finally:
+            os.environ.pop("B200MSDF_HOST_FLAT")
+        return general, prep.prepare(shapes, **kw)
+
+    def same(a, b):
+        return (all(np.array_equal(getattr(a, k), getattr(b, k)) for k in ("gbegin", "cbegin", "orders", "colors"))
+                and np.array_equal(a.points.view(np.uint64), b.points.view(np.uint64)))
+
+    fuzz = FlatShapes.concat([FlatShapes.single(*fuzz_shape(seed)[1:5]) for seed in range(108)])
+    for shapes in (synth_atlas(600, seed=78, cubic_fraction=0.3), synth_atlas(600, seed=79), fuzz):
+        for coloring in ("simple", "inktrap", None):
+            for normalize in (True, False):
+                for seed in (0, 5, 12345678901):
+                    a, b = both(shapes, coloring=coloring, normalize=normalize, seed=seed)
+                    assert same(a, b), (coloring, normalize, seed)
