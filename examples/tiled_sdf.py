@@ -33,7 +33,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     shape = prep.prepare(synth_big_shape(args.contours, args.segments)) if rank == 0 else None
     if world > 1:
-        shape = tiled.broadcast_shape(shape, 0, torch.device("cuda", local))
+        shape, _ = tiled.broadcast_shape(shape, 0, torch.device("cuda", local))
     xf = glyph_transform(args.size, px_range=8.0)
     ctx = api.Context(local)
     tiled.generate_band(ctx, api.SDF, shape, xf, args.size, args.size, rank, world)     # warm-up: module load, buffer growth

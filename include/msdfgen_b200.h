@@ -181,7 +181,10 @@ int b200msdf_simulate_8bit(b200msdf_ctx *ctx, const b200msdf_bitmap *bitmap, int
 
 /* Uploads shapes + per-glyph geometry and allocates outputs. dims: [2] shared (w,h) or [2*n_glyphs] (dims_per_glyph != 0).
  * out_y_downward: [n_glyphs] or NULL.  Output layout: glyph g is a packed [h][w][N] float block at
- * b200msdf_batch_glyph_offset(batch, g) floats from the start of the output buffer (offsets are multiples of 4 floats). */
+ * b200msdf_batch_glyph_offset(batch, g) floats from the start of the output buffer (offsets are multiples of 4 floats).
+ * INPUT LIFETIME: the copies out of the caller's arrays are enqueued on the context's stream; when those arrays are pinned
+ * (page-locked) memory the call returns before they have been read, so they must stay untouched until the stream has drained
+ * (b200msdf_synchronize, or any later host-buffer call on this context).  Pageable arrays are consumed before the call returns. */
 int b200msdf_batch_upload(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
                           int transform_per_glyph, const int32_t *dims, int dims_per_glyph, const uint8_t *out_y_downward,
                           b200msdf_batch **batch);

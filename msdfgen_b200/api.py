@@ -173,6 +173,13 @@ class Context:
         buf = (C.c_uint8 * max(count * dtype.itemsize, 1)).from_address(ptr.value)
         return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
+    def release_pinned(self):
+        """Frees every block handed out by pinned() (the arrays must no longer be used)."""
+        self.synchronize()
+        for p in self._pinned:
+            self.lib.b200msdf_host_free(p)
+        self._pinned = []
+
     # ---- reference-shaped single-shape calls ----------------------------------------------------------------------
     def generate(self, mode, output, shape: FlatShapes, transformation, config: MSDFGeneratorConfig = None, out_ydown=False,
                  ec_buffer=None):

@@ -110,6 +110,7 @@ struct b200msdf_batch {
     bool ecRan = false;
     float *current = nullptr;       // device pointer to the most recent result (raw field after k1, final output after a full launch)
     DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, bigCull, bigPerp, field, out, stencil, candidates, candCount;
+    DevBuf signMatch;             // scanline pass of multi-channel fields: per-texel match flags (never the EC stencil)
     DevBuf bytes, byteTargets;    // 8-bit output path
     DevBuf blocks, blockWork;     // big shapes: 2-D block tiles of k1_big_blocks and its per-CTA list / cap workspace
     int nBlocks = 0, maxBigSegs = 0, maxBigContours = 0;
@@ -120,7 +121,7 @@ struct b200msdf_batch {
     std::vector<int> hBig;
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
-        bigGlyphs.release(); bigRecs.release(); bigCull.release(); bigPerp.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); bytes.release(); byteTargets.release();
+        bigGlyphs.release(); bigRecs.release(); bigCull.release(); bigPerp.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); bytes.release(); byteTargets.release(); signMatch.release();
         blocks.release(); blockWork.release();
     }
 };
@@ -133,6 +134,9 @@ struct b200msdf_ctx {
     PinBuf pinOut, pinIn, pinDesc;  // pinDesc: staging of per-batch descriptors (glyphs, tiles) so that their H2D copies are true async DMAs
     cudaEvent_t descDone = nullptr; // the last copy out of pinDesc
     uint64_t launches = 0;
+    // resident CTAs per SM of every kernel launched through this context, and the dynamic-shared-memory opt-in that goes with
+    // it: both are per DEVICE, and a context is bound to one device
+    std::unordered_map<const void *, int> occupancy;
     b200msdf_batch pool;        // reused by the host-buffer entry points
     b200msdf_batch chunk[2];    // reused by the chunked host path
     b200msdf_batch *cur = nullptr;
@@ -168,6 +172,12 @@ int check_shapes(const b200msdf_shapes *s) {
             return fail(B200MSDF_ERR_ARG, "contour_segment_begin not monotonic at %d", c);
     if (s->contour_segment_begin && s->contour_segment_begin[s->n_contours] > (uint32_t) s->n_segments)
         return fail(B200MSDF_ERR_ARG, "contour_segment_begin exceeds n_segments");
+    // EdgeSegment::type(): 1, 2 or 3 — anything else would index past the control points on the device
+    unsigned bad = 0;
+    for (int i = 0; i < s->n_segments; ++i)
+        bad |= (unsigned) (s->orders[i]-1u) > 2u;
+    if (bad)
+        return fail(B200MSDF_ERR_ARG, "orders must be 1 (linear), 2 (quadratic) or 3 (cubic)");
     return 0;
 }
 
@@ -350,8 +360,9 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
 
 template <typename K>
 int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, size_t dynSmem, int threads, int *grid) {
-    // resident CTAs per SM of this kernel: queried once per kernel and cached (the query costs microseconds per launch)
-    static thread_local std::unordered_map<const void *, int> cache;
+    // resident CTAs per SM of this kernel on this context's device: queried once and cached (the query costs microseconds
+    // per launch); cudaFuncSetAttribute is per device too, so the cache lives in the context
+    std::unordered_map<const void *, int> &cache = ctx->occupancy;
     int perSM = 0;
     auto it = cache.find((const void *) kernel);
     if (it != cache.end())
@@ -533,9 +544,13 @@ int launch_sign(b200msdf_ctx *ctx, b200msdf_batch *b, KernelParams &P, const flo
     if (b->N >= 3 && b->regions)
         return fail(B200MSDF_ERR_ARG, "multi-channel sign correction is not available for region batches (needs neighbouring tiles)");
     int *ambiguous = b->counters.as<int>()+8;
-    int8_t *match = b->N >= 3 ? b->stencil.as<int8_t>() : nullptr;
-    if (b->N >= 3)
+    int8_t *match = nullptr;
+    if (b->N >= 3) {
+        int rc = b->signMatch.reserve(b->texels+64);
+        if (rc) return rc;
+        match = b->signMatch.as<int8_t>();
         CUDA_TRY(cudaMemsetAsync(ambiguous, 0, sizeof(int), ctx->stream));
+    }
     switch (b->N) {
         case 1: k5_scanline_sign<1><<<b->nTiles, CTA_THREADS, 0, ctx->stream>>>(P, src, dst, match, ambiguous, zero, fillRule); break;
         case 3: k5_scanline_sign<3><<<b->nTiles, CTA_THREADS, 0, ctx->stream>>>(P, src, dst, match, ambiguous, zero, fillRule); break;
@@ -606,7 +621,9 @@ int download_to_bitmaps(b200msdf_ctx *ctx, b200msdf_batch *b, const float *dSrc,
         const GlyphDesc &d = b->hGlyphs[(size_t) g];
         if ((size_t) d.w*d.h == 0)
             continue;
-        if (bm[g].row_stride != d.w*N || bm[g].pixels != bm[0].pixels+(d.outOffset-b->hGlyphs[0].outOffset))
+        // (device offsets are padded to 4 floats: a glyph whose float count is not a multiple of 4 would drag padding into
+        // caller memory that belongs to no bitmap)
+        if (bm[g].row_stride != d.w*N || bm[g].pixels != bm[0].pixels+(d.outOffset-b->hGlyphs[0].outOffset) || (((size_t) d.w*d.h*N)&3))
             packed = false;
     }
     if (packed && bm[0].pixels) {
@@ -855,7 +872,9 @@ int b200msdf_generate_batch(b200msdf_ctx *ctx, int mode, const b200msdf_shapes *
     float *direct = nullptr;
     if (packed_outputs(outputs, n, channels_of(mode)) && !getenv("B200MSDF_NO_ZEROCOPY")) {
         cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, outputs[0].pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+        // (the kernels write float4 rows: a packed block that starts at a 4-, 8- or 12-byte offset takes the staged path)
+        if (cudaPointerGetAttributes(&attr, outputs[0].pixels) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer &&
+            (reinterpret_cast<uintptr_t>(attr.devicePointer)&15) == 0)
             direct = static_cast<float *>(attr.devicePointer);
         else
             cudaGetLastError();

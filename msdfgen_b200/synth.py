@@ -31,18 +31,20 @@ def _ring(rng, cx, cy, radius, n, clockwise, cubic_fraction, linear_fraction=0.5
     mx, my = 0.5 * (vx + nx), 0.5 * (vy + ny)
     bulge = rng.uniform(-0.3, 0.3, n)
     bulge2 = rng.uniform(-0.3, 0.3, n)
-    for i in range(n):
-        if kind[i] < linear_fraction:
-            pts[i, 0:4] = (vx[i], vy[i], nx[i], ny[i])
-        elif kind[i] < 1.0 - cubic_fraction:
-            orders[i] = 2
-            pts[i, 0:6] = (vx[i], vy[i], mx[i] - bulge[i] * dy[i], my[i] + bulge[i] * dx[i], nx[i], ny[i])
-        else:
-            orders[i] = 3
-            pts[i] = (vx[i], vy[i],
-                      vx[i] + dx[i] / 3 - bulge[i] * dy[i], vy[i] + dy[i] / 3 + bulge[i] * dx[i],
-                      vx[i] + 2 * dx[i] / 3 - bulge2[i] * dy[i], vy[i] + 2 * dy[i] / 3 + bulge2[i] * dx[i],
-                      nx[i], ny[i])
+    # (vectorised; element for element the same IEEE expressions as a per-edge loop)
+    lin = kind < linear_fraction
+    quad = ~lin & (kind < 1.0 - cubic_fraction)
+    cub = ~lin & ~quad
+    pts[:, 0], pts[:, 1] = vx, vy
+    pts[lin, 2], pts[lin, 3] = nx[lin], ny[lin]
+    orders[quad] = 2
+    pts[quad, 2], pts[quad, 3] = (mx - bulge * dy)[quad], (my + bulge * dx)[quad]
+    pts[quad, 4], pts[quad, 5] = nx[quad], ny[quad]
+    if cub.any():
+        orders[cub] = 3
+        pts[cub, 2], pts[cub, 3] = (vx + dx / 3 - bulge * dy)[cub], (vy + dy / 3 + bulge * dx)[cub]
+        pts[cub, 4], pts[cub, 5] = (vx + 2 * dx / 3 - bulge2 * dy)[cub], (vy + 2 * dy / 3 + bulge2 * dx)[cub]
+        pts[cub, 6], pts[cub, 7] = nx[cub], ny[cub]
     return pts, orders
 
 
@@ -92,3 +94,28 @@ def glyph_transform(w, h=None, px_range=4.0):
     h = w if h is None else h
     rng = px_range / w
     return np.array([float(w), float(h), 0.0, 0.0, -0.5 * rng, 0.5 * rng], dtype=np.float64)
+
+
+def glyph_segment_counts(n_glyphs, seed=0xB200, min_segments=8, max_segments=64):
+    """Segment count of every glyph of synth_atlas(n_glyphs, seed) without building it (the first draw of each glyph's stream) —
+    the cost estimate used to shard a large atlas before any rank has synthesised its part."""
+    return np.array([int(np.random.Generator(np.random.PCG64(seed + i)).integers(min_segments, max_segments + 1)) for i in range(n_glyphs)],
+                    dtype=np.int64)
+
+
+def _synth_range(args):
+    g0, g1, seed, kw = args
+    return FlatShapes.concat([synth_glyph(seed + i, **kw) for i in range(g0, g1)])
+
+
+def synth_atlas_range(g0, g1, seed=0xB200, workers=1, **kw):
+    """Glyphs [g0, g1) of synth_atlas(*, seed): identical arrays, optionally built by `workers` forked processes (call before CUDA
+    is initialised in this process)."""
+    n = g1 - g0
+    if workers <= 1 or n < 2048:
+        return _synth_range((g0, g1, seed, kw))
+    import multiprocessing as mp
+    step = max(512, -(-n // (workers * 4)))
+    jobs = [(a, min(a + step, g1), seed, kw) for a in range(g0, g1, step)]
+    with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+        return FlatShapes.concat(pool.map(_synth_range, jobs))

@@ -18,28 +18,58 @@ def band(height, rank, world):
     return r0, r0 + base + (1 if rank < extra else 0)
 
 
+_NAMES = ("gbegin", "cbegin", "points", "orders", "colors", "ydown")
+_DTYPES = (np.uint32, np.uint32, np.float64, np.uint8, np.uint8, np.uint8)
+
+
+def pack_shape(shape: FlatShapes) -> np.ndarray:
+    """The flat shape arrays as ONE byte buffer: int64[8] header (element counts of the six arrays), then the arrays back to
+    back, each padded to 16 bytes.  This is what crosses NVLink — a single broadcast of the shared segment pool."""
+    arrays = [np.ascontiguousarray(getattr(shape, n), dtype=dt).reshape(-1) for n, dt in zip(_NAMES, _DTYPES)]
+    header = np.zeros(8, np.int64)
+    header[:6] = [a.size for a in arrays]
+    chunks = [header.view(np.uint8)]
+    for a in arrays:
+        raw = a.view(np.uint8)
+        chunks += [raw, np.zeros((-raw.size) % 16, np.uint8)]
+    return np.concatenate(chunks)
+
+
+def packed_size(header) -> int:
+    return 64 + sum(int(-(-int(n) * np.dtype(dt).itemsize // 16) * 16) for n, dt in zip(header[:6], _DTYPES))
+
+
+def unpack_shape(buf: np.ndarray) -> FlatShapes:
+    header = buf[:64].view(np.int64)
+    out, off = {}, 64
+    for n, dt, count in zip(_NAMES, _DTYPES, header[:6]):
+        nbytes = int(count) * np.dtype(dt).itemsize
+        a = buf[off:off + nbytes].view(dt)
+        out[n] = a.reshape(-1, 8) if n == "points" else a
+        off += -(-nbytes // 16) * 16
+    return FlatShapes(**out)
+
+
 def broadcast_shape(shape: FlatShapes | None, src=0, device=None):
-    """torch.distributed broadcast of the flat shape arrays from rank `src` (NCCL when `device` is a CUDA device, else gloo)."""
+    """Rank `src` sends the packed shape to every rank: an 8-word size header, then ONE broadcast of the byte buffer (NCCL over
+    NVLink when `device` is a CUDA device, gloo otherwise).  Returns (FlatShapes, payload bytes)."""
     import torch
     import torch.distributed as dist
     rank = dist.get_rank()
-    names = ("gbegin", "cbegin", "points", "orders", "colors", "ydown")
-    meta = [None]
+    dev = device if device is not None else "cpu"
     if rank == src:
-        meta = [[(getattr(shape, n).shape, str(getattr(shape, n).dtype)) for n in names]]
-    dist.broadcast_object_list(meta, src=src)
-    out = {}
-    for n, (shp, dt) in zip(names, meta[0]):
-        if rank == src:
-            a = np.ascontiguousarray(getattr(shape, n))
-            t = torch.from_numpy(a.view(np.uint8).reshape(-1).copy())
-        else:
-            t = torch.empty(int(np.prod(shp)) * np.dtype(dt).itemsize, dtype=torch.uint8)
-        if device is not None:
-            t = t.to(device)
-        dist.broadcast(t, src=src)
-        out[n] = t.cpu().numpy().view(np.dtype(dt)).reshape(shp)
-    return FlatShapes(**out)
+        packed = pack_shape(shape)
+        header = torch.from_numpy(packed[:64].view(np.int64).copy()).to(dev)
+    else:
+        header = torch.zeros(8, dtype=torch.int64, device=dev)
+    dist.broadcast(header, src=src)
+    size = packed_size(header.cpu().numpy())
+    if rank == src:
+        payload = torch.from_numpy(packed).to(dev)
+    else:
+        payload = torch.empty(size, dtype=torch.uint8, device=dev)
+    dist.broadcast(payload, src=src)
+    return unpack_shape(payload.cpu().numpy()), size
 
 
 def generate_band(ctx: api.Context, mode, shape: FlatShapes, transformation, width, height, rank, world, config=None):

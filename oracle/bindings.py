@@ -116,7 +116,14 @@ class Oracle:
             return {"kind": "port", "omp": False, "threads": 1}
         omp, thr = C.c_int(0), C.c_int(0)
         ver = self.lib.ref_info(C.byref(omp), C.byref(thr))
-        return {"kind": "reference", "version": ver, "omp": bool(omp.value), "threads": thr.value}
+        return {"kind": "reference", "version": ver, "omp": bool(omp.value), "omp_level": omp.value, "threads": thr.value}
+
+    def set_threads(self, n):
+        """OpenMP team size of this library's parallel regions (no-op for the single-threaded builds); returns the size in effect."""
+        if not self.is_ref:
+            return 1
+        self.lib.ref_set_threads.restype = C.c_int
+        return int(self.lib.ref_set_threads(C.c_int(int(n))))
 
     # -- generators --------------------------------------------------------------------------------------------------
     def generate(self, mode, cbegin, points, orders, colors, xf, w, h, cfg: Config = Config(), shape_ydown=False,

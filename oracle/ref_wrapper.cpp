@@ -114,7 +114,12 @@ int generateOne(int mode, const Shape &shape, const SDFTransformation &t, float 
 extern "C" {
 
 int ref_info(int *ompEnabled, int *maxThreads) {
-#ifdef MSDFGEN_USE_OPENMP
+    // ompEnabled: 2 = the reference's own row-parallel pragmas are compiled in (MSDFGEN_USE_OPENMP), 1 = only this wrapper's
+    // outer loops are parallel (glyph-parallel harness), 0 = single-threaded build.  maxThreads = what an OpenMP region would use.
+#if defined(MSDFGEN_USE_OPENMP)
+    *ompEnabled = 2;
+    *maxThreads = omp_get_max_threads();
+#elif defined(_OPENMP)
     *ompEnabled = 1;
     *maxThreads = omp_get_max_threads();
 #else
@@ -122,6 +127,19 @@ int ref_info(int *ompEnabled, int *maxThreads) {
     *maxThreads = 1;
 #endif
     return MSDFGEN_VERSION_MAJOR*10000+MSDFGEN_VERSION_MINOR*100+MSDFGEN_VERSION_REVISION;
+}
+
+/// Sets the OpenMP team size of this build's parallel regions (the environment may have been read before the caller could set
+/// OMP_NUM_THREADS — e.g. torchrun exports OMP_NUM_THREADS=1); returns what a region will now use.
+int ref_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0)
+        omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void) n;
+    return 1;
+#endif
 }
 
 /// generate{SDF,PSDF,MSDF,MTSDF}(BitmapSection, Shape, SDFTransformation, config) for one shape.
@@ -235,6 +253,12 @@ int ref_oneshot_distance(int mode, int overlap, int nContours, const uint32_t *c
                          int nPts, const double *pts, double *out) {
     Shape shape;
     buildShape(shape, nContours, cbegin, points, orders, colors, 0);
+    if (mode < 1 || mode > 4)
+        return -1;
+    // (independent query points: the glyph-parallel harness build spreads them over the host threads)
+#ifdef _OPENMP
+    #pragma omp parallel for schedule(dynamic, 64)
+#endif
     for (int i = 0; i < nPts; ++i) {
         Point2 p(pts[2*i], pts[2*i+1]);
         switch (mode) {
@@ -258,8 +282,6 @@ int ref_oneshot_distance(int mode, int overlap, int nContours, const uint32_t *c
                 out[4*i] = d.r, out[4*i+1] = d.g, out[4*i+2] = d.b, out[4*i+3] = d.a;
                 break;
             }
-            default:
-                return -1;
         }
     }
     return 0;

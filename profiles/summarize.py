@@ -31,7 +31,7 @@ for kernel in ("k1_distance_field", "k2_classify", "k3_exact_distance", "k1_big_
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
-    what = ("one launch of `SIZE=2048 MODE=1 python tests/_gpu_big_one.py`: the 10k-segment shape, sdf 2048x2048, overlapping combiner"
+    what = ("one launch of `SIZE=2048 MODE=1 python tools/_gpu_big_one.py`: the 10k-segment shape, sdf 2048x2048, overlapping combiner"
             if kernel == "k1_big_blocks" else "one launch of `python bench.py --steps 1 --warmup 3`, 4096 glyphs msdf 32x32")
     lines = [f"# {kernel} — ncu --set full --clock-control none ({what})",
              f"# kernel: {vals[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else kernel}", ""]

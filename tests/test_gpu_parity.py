@@ -253,14 +253,14 @@ def test_mtsdf64_config3_sample(ctx, port):
 def test_full_atlas_against_compiled_reference(ctx):
     """BASELINE configs[1] and [2] at FULL size against the unmodified reference (possible because the compiled reference
     runs glyph-parallel on the box's host cores in about a second): every one of the 12.6 M (msdf 32x32) and 67 M
-    (mtsdf 64x64, first 1024 glyphs) floats within 1e-4, identical bytes; the number of differing bit patterns is printed."""
+    (mtsdf 64x64 = BASELINE configs[2] at full size, 268 M floats) floats within 1e-4, identical bytes; the number of differing bit patterns is printed."""
     from oracle import bindings
     if not bindings.ref_available(kind="reference_gp"):
         pytest.skip("compiled reference (oracle/_ref) did not travel to this box")
     ref = bindings.Oracle("reference_gp")
     n = 4096
     atlas = prep.prepare(synth_atlas(n))
-    for mode_name, mode, w, count in (("msdf", api.MSDF, 32, n), ("mtsdf", api.MTSDF, 64, 1024), ("psdf", api.PSDF, 32, n)):
+    for mode_name, mode, w, count in (("msdf", api.MSDF, 32, n), ("mtsdf", api.MTSDF, 64, n), ("psdf", api.PSDF, 32, n)):
         sub = atlas.slice(0, count)
         xf = glyph_transform(w)
         got = np.empty((count, w, w, api.CHANNELS[mode]), np.float32)
@@ -307,6 +307,93 @@ def test_config4_big_shape_tiles_and_oracle_samples(ctx):
     d = oracle.distance("psdf", True, cb, p, od, cl, pts)[:, 0]
     want = (np.float64(1.0) / (xfp[5] - xfp[4]) * (d + (-xfp[4]))).astype(np.float32)
     assert_parity(fullp[ys, xs, 0], want, "config-4 psdf samples")
+
+
+def test_config4_full_size_bands_and_oracle(ctx):
+    """BASELINE configs[3] at FULL size (10k segments, sdf 4096x4096, default overlap support): the eight row bands of an 8-GPU run
+    (generated here one after the other as regions) are bit-identical to the untiled image; 100 000 random texels per band-set
+    equal ShapeDistanceFinder::oneShotDistance of the compiled reference (/root/reference/core/ShapeDistanceFinder.hpp:36-58,
+    SURVEY.md App. B.9); and a full 1024x1024 image equals the reference's own OpenMP generateSDF texel for texel."""
+    from oracle import bindings
+    from msdfgen_b200 import tiled
+    if not bindings.ref_available(kind="reference_gp"):
+        pytest.skip("compiled reference (oracle/_ref) did not travel to this box")
+    shape = prep.prepare(synth_big_shape(100, 100))
+    size, world = 4096, 8
+    xf = glyph_transform(size, px_range=8.0)
+    batch = ctx.upload(api.SDF, shape, xf, [size, size])
+    batch.launch(api.MSDFGeneratorConfig())
+    full = batch.download()[: size * size].reshape(size, size)
+    batch.free()
+    for r in range(world):
+        b, (r0, r1) = tiled.generate_band(ctx, api.SDF, shape, xf, size, size, r, world)
+        assert np.array_equal(b[..., 0].view(np.uint32), full[r0:r1].view(np.uint32)), f"band {r} differs from the untiled image"
+    gp = bindings.Oracle("reference_gp")
+    rng = np.random.default_rng(44)
+    n = 100000
+    xs, ys = rng.integers(0, size, n), rng.integers(0, size, n)
+    pts = np.stack([(xs + .5) / xf[0] - xf[2], (ys + .5) / xf[1] - xf[3]], axis=1)
+    cb, p, od, cl, _ = shape.glyph(0)
+    d = gp.distance("sdf", True, cb, p, od, cl, pts)[:, 0]
+    want = (np.float64(1.0) / (xf[5] - xf[4]) * (d + (-xf[4]))).astype(np.float32)
+    bits = assert_parity(full[ys, xs], want, "config-4 full-size samples")
+    print(f"[parity] config 4, 4096x4096: {bits} of {n} sampled texels differ in bit pattern")
+    # one whole image by the reference's own row-parallel OpenMP generator
+    small = 1024
+    xfs = glyph_transform(small, px_range=8.0)
+    got = np.empty((small, small, 1), np.float32)
+    ctx.generate(api.SDF, got, shape, xfs)
+    want = bindings.Oracle("reference_omp").generate("sdf", cb, p, od, cl, xfs, small, small)
+    bits = assert_parity(got, want, "config-4 1024x1024 full image")
+    print(f"[parity] config 4, 1024x1024 full image: {bits} of {got.size} floats differ in bit pattern")
+
+
+def test_config5_shard_of_the_65536_glyph_atlas(ctx):
+    """BASELINE configs[4]: the 65536-glyph atlas sharded over 8 ranks exactly as bench.py does it (cost-balanced contiguous
+    ranges from the glyphs' segment counts).  The ranges tile the atlas; one whole shard (rank 5 of 8, ~8192 glyphs) is generated
+    and compared with the compiled reference float for float."""
+    from oracle import bindings
+    from msdfgen_b200 import shard
+    from msdfgen_b200.synth import glyph_segment_counts, synth_atlas_range
+    if not bindings.ref_available(kind="reference_gp"):
+        pytest.skip("compiled reference (oracle/_ref) did not travel to this box")
+    n, world, rank, w = 65536, 8, 5, 32
+    costs = glyph_segment_counts(n, 0xB200) * w * w
+    b = shard.partition(costs, world)
+    assert b[0] == 0 and b[-1] == n and (np.diff(b) > 0).all()
+    per = np.array([costs[b[r]:b[r + 1]].sum() for r in range(world)], dtype=np.float64)
+    assert per.max() / per.mean() < 1.01          # balanced to 1 %
+    g0, g1 = int(b[rank]), int(b[rank + 1])
+    atlas = prep.prepare(synth_atlas_range(g0, g1, 0xB200))
+    xf = glyph_transform(w)
+    got = np.empty((g1 - g0, w, w, 3), np.float32)
+    ctx.generate_batch(api.MSDF, got, atlas, xf)
+    want, _ = bindings.Oracle("reference_gp").generate_batch("msdf", atlas.gbegin, atlas.cbegin, atlas.points, atlas.orders, atlas.colors, xf, w, w,
+                                                             glyph_parallel=True)
+    bits = assert_parity(got, want, f"config-5 shard {rank}/{world}")
+    print(f"[parity] config 5 shard {rank}/{world} ({g1 - g0} glyphs): {bits} of {got.size} floats differ in bit pattern")
+
+
+def test_misaligned_pinned_block_and_bad_orders(ctx):
+    """A packed pinned block that does not start on a 16-byte boundary must not take the float4 zero-copy path (ADVICE r1);
+    segment orders outside 1..3 are rejected on the host."""
+    atlas = prep.prepare(synth_atlas(64, seed=99))
+    xf = glyph_transform(32)
+    want = np.empty((64, 32, 32, 3), np.float32)
+    ctx.generate_batch(api.MSDF, want, atlas, xf)
+    raw = ctx.pinned((64 * 32 * 32 * 3 + 4,), np.float32)
+    for off in (1, 2, 3):
+        view = raw[off:off + 64 * 32 * 32 * 3].reshape(64, 32, 32, 3)
+        view[...] = np.nan
+        ctx.generate_batch(api.MSDF, view, atlas, xf)
+        assert np.array_equal(np.asarray(view).view(np.uint32), want.view(np.uint32)), off
+    bad = FlatShapes(atlas.gbegin, atlas.cbegin, atlas.points, atlas.orders.copy(), atlas.colors, atlas.ydown)
+    bad.orders[5] = 0
+    with pytest.raises(Exception):
+        ctx.generate_batch(api.MSDF, want, bad, xf)
+    bad.orders[5] = 4
+    with pytest.raises(Exception):
+        ctx.generate_batch(api.MSDF, want, bad, xf)
 
 
 def test_regions_reject_error_correction(ctx):

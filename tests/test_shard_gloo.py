@@ -84,7 +84,8 @@ def _bcast_worker(rank, world, port, q):
     from msdfgen_b200 import tiled
     from msdfgen_b200.synth import synth_big_shape
     shape = synth_big_shape(5, 7) if rank == 0 else None
-    got = tiled.broadcast_shape(shape, 0, None)
+    got, nbytes = tiled.broadcast_shape(shape, 0, None)
+    assert nbytes == tiled.pack_shape(got).size
     want = synth_big_shape(5, 7)
     ok = all(np.array_equal(getattr(got, n), getattr(want, n)) for n in ("gbegin", "cbegin", "points", "orders", "colors", "ydown"))
     oks = [None] * world
