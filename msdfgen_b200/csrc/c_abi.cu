@@ -115,6 +115,9 @@ struct b200msdf_batch {
     DevBuf blocks, blockWork;     // big shapes: 2-D block tiles of k1_big_blocks and its per-CTA list / cap workspace
     int nBlocks = 0, maxBigSegs = 0, maxBigContours = 0;
     std::vector<TileDesc> hBlocks;
+    DevBuf filt, tileFilt;        // k1a -> k1b filter words (sized at launch) and the small tiles' word offsets: [overlap][tile], [simple][tile]
+    size_t filtWords[2] = { 0, 0 };
+    std::vector<unsigned long long> hTileFilt;
     DevBuf counters, scratch;     // per batch, so that batches launched on different streams never share scheduling state
     std::vector<GlyphDesc> hGlyphs;
     std::vector<TileDesc> hTiles;
@@ -122,7 +125,7 @@ struct b200msdf_batch {
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
         bigGlyphs.release(); bigRecs.release(); bigCull.release(); bigPerp.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); bytes.release(); byteTargets.release(); signMatch.release();
-        blocks.release(); blockWork.release();
+        blocks.release(); blockWork.release(); filt.release(); tileFilt.release();
     }
 };
 
@@ -287,6 +290,45 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
         b->hTiles.swap(sorted);
     }
     b->nSmallTiles = (int) b->hTiles.size();
+    // filter words of the small tiles (k1a_filter -> k1b_exact), for the overlapping and for the simple combiner: per unit of
+    // 32 texels 32 x words(glyph) — the unit count mirrors UnitGrid in kernels.cuh
+    {
+        const size_t nT = b->hTiles.size();
+        b->hTileFilt.resize(2*nT);
+        std::vector<unsigned> wordsOv((size_t) s->n_glyphs), wordsSimple((size_t) s->n_glyphs);
+        for (int g = 0; g < s->n_glyphs; ++g) {
+            const GlyphDesc &d = b->hGlyphs[(size_t) g];
+            unsigned ov = 0;
+            for (unsigned c = d.c0; c < d.c1; ++c) {
+                unsigned n = s->contour_segment_begin[c+1]-s->contour_segment_begin[c];
+                if (n)
+                    ov += mode == 1 ? filter_words_group<1>(n) : mode == 2 ? filter_words_group<2>(n) : filter_words_group<3>(n);
+            }
+            unsigned n = d.s1-d.s0;
+            wordsOv[(size_t) g] = ov;
+            wordsSimple[(size_t) g] = !n ? 0u : mode == 1 ? filter_words_group<1>(n) : mode == 2 ? filter_words_group<2>(n) : filter_words_group<3>(n);
+        }
+        size_t offOv = 0, offSimple = 0;
+        for (size_t t = 0; t < nT; ++t) {
+            const TileDesc &td = b->hTiles[t];
+            const GlyphDesc &d = b->hGlyphs[td.glyph];
+            const size_t total = (size_t) d.w*(size_t) d.h;
+            const size_t pixEnd = td.pix0+TILE_PIXELS < total ? td.pix0+TILE_PIXELS : total;
+            const bool blocked = (d.w&7) == 0 && d.w <= TILE_PIXELS && (TILE_PIXELS%d.w) == 0;
+            size_t units;
+            if (blocked) {
+                size_t nRows = (pixEnd-td.pix0)/(size_t) d.w;
+                units = (size_t) (d.w>>3)*((nRows+3)>>2);
+            } else
+                units = (pixEnd-td.pix0+31)>>5;
+            b->hTileFilt[t] = offOv;
+            b->hTileFilt[nT+t] = offSimple;
+            offOv += units*32*wordsOv[td.glyph];
+            offSimple += units*32*wordsSimple[td.glyph];
+        }
+        b->filtWords[0] = offOv;
+        b->filtWords[1] = offSimple;
+    }
     b->hTiles.insert(b->hTiles.end(), bigTiles.begin(), bigTiles.end());
     b->outFloats = outFloats;
     b->texels = texels;
@@ -305,6 +347,7 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     if ((rc = b->windings.reserve(nCon+16))) return rc;
     if ((rc = b->glyphs.reserve(sizeof(GlyphDesc)*(b->hGlyphs.size()+1)))) return rc;
     if ((rc = b->tiles.reserve(sizeof(TileDesc)*(b->hTiles.size()+1)))) return rc;
+    if ((rc = b->tileFilt.reserve(sizeof(unsigned long long)*(b->hTileFilt.size()+1)))) return rc;
     if ((rc = b->out.reserve(outFloats*4+64))) return rc;
     if ((rc = b->counters.reserve(64))) return rc;
     if (b->N >= 3) {
@@ -337,10 +380,11 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     // synchronous on the host)
     {
         const size_t gBytes = sizeof(GlyphDesc)*b->hGlyphs.size(), tBytes = sizeof(TileDesc)*b->hTiles.size();
+        const size_t fBytes = sizeof(unsigned long long)*b->hTileFilt.size();
         if (gBytes+tBytes) {
             if (ctx->descDone)
                 CUDA_TRY(cudaEventSynchronize(ctx->descDone));      // an earlier batch may still be reading the staging buffer
-            if ((rc = ctx->pinDesc.reserve(gBytes+tBytes+64))) return rc;
+            if ((rc = ctx->pinDesc.reserve(gBytes+tBytes+fBytes+64))) return rc;
             char *stage = static_cast<char *>(ctx->pinDesc.p);
             if (gBytes) {
                 memcpy(stage, b->hGlyphs.data(), gBytes);
@@ -349,6 +393,10 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
             if (tBytes) {
                 memcpy(stage+gBytes, b->hTiles.data(), tBytes);
                 CUDA_TRY(cudaMemcpyAsync(b->tiles.p, stage+gBytes, tBytes, cudaMemcpyHostToDevice, st));
+            }
+            if (fBytes) {
+                memcpy(stage+gBytes+tBytes, b->hTileFilt.data(), fBytes);
+                CUDA_TRY(cudaMemcpyAsync(b->tileFilt.p, stage+gBytes+tBytes, fBytes, cudaMemcpyHostToDevice, st));
             }
             if (!ctx->descDone)
                 CUDA_TRY(cudaEventCreateWithFlags(&ctx->descDone, cudaEventDisableTiming));
@@ -402,7 +450,20 @@ template <int MODE, bool OVERLAP>
 int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
     int rc;
     P.tileBegin = 0; P.tileEnd = P.nSmallTiles; P.counterIndex = 0;
-    if ((rc = launch_tiles(ctx, k1_distance_field<MODE, OVERLAP, false>, P, scratch))) return rc;
+    if (getenv("B200MSDF_K1_LEGACY")) {
+        if ((rc = launch_tiles(ctx, k1_distance_field<MODE, OVERLAP, false>, P, scratch))) return rc;
+    } else if (P.nSmallTiles > 0) {
+        // k1a_filter (fp32 bounds -> survivor masks) then k1b_exact (fp64 evaluation of the survivors + contour combiner)
+        b200msdf_batch *bb = ctx->cur;
+        const size_t words = bb->filtWords[OVERLAP ? 0 : 1];
+        if ((rc = bb->filt.reserve(words*sizeof(unsigned)+256))) return rc;
+        P.filt = bb->filt.as<unsigned>();
+        P.tileFilt = bb->tileFilt.as<unsigned long long>()+(OVERLAP ? 0 : (size_t) P.nSmallTiles);
+        P.counterIndex = 5;
+        if ((rc = launch_tiles(ctx, k1a_filter<MODE, OVERLAP>, P, 0, 0, K1_THREADS))) return rc;
+        P.counterIndex = 0;
+        if ((rc = launch_tiles(ctx, k1b_exact<MODE, OVERLAP>, P, scratch, 0, K1_THREADS))) return rc;
+    }
     // big shapes: 2-D blocks with per-block record lists; each resident CTA owns a slice of the list / cap workspace
     b200msdf_batch *b = ctx->cur;
     if (b->nBlocks > 0) {

@@ -31,19 +31,32 @@ __device__ __forceinline__ d2 operator-(d2 a, d2 b) { return mk(a.x-b.x, a.y-b.y
 __device__ __forceinline__ d2 operator*(double s, d2 a) { return mk(s*a.x, s*a.y); }
 __device__ __forceinline__ double dot(d2 a, d2 b) { return a.x*b.x+a.y*b.y; }
 __device__ __forceinline__ double cross(d2 a, d2 b) { return a.x*b.y-a.y*b.x; }
-__device__ __forceinline__ double len(d2 a) { return sqrt(a.x*a.x+a.y*a.y); }
+// IEEE fp64 square root and division expand to 25-30 instructions each; the distance kernels issue them from dozens of sites.
+// B200_COMPACT_MATH=1 routes them through two out-of-line functions (same correctly rounded results), which keeps the kernels'
+// hot code inside the 32 KB L1.5 instruction cache.
+#ifndef B200_COMPACT_MATH
+#define B200_COMPACT_MATH 1
+#endif
+#if B200_COMPACT_MATH
+__device__ __noinline__ double dsqrt(double x) { return sqrt(x); }
+__device__ __noinline__ double ddiv(double a, double b) { return a/b; }
+#else
+__device__ __forceinline__ double dsqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double ddiv(double a, double b) { return a/b; }
+#endif
+__device__ __forceinline__ double len(d2 a) { return dsqrt(a.x*a.x+a.y*a.y); }
 __device__ __forceinline__ bool is_zero(d2 a) { return a.x == 0 && a.y == 0; }
 // Vector2::normalize(allowZero): zero vector -> (0, !allowZero)
 __device__ __forceinline__ d2 normalize(d2 a, bool allowZero) {
     double l = len(a);
     if (l != 0)
-        return mk(a.x/l, a.y/l);
+        return mk(ddiv(a.x, l), ddiv(a.y, l));
     return mk(0, allowZero ? 0.0 : 1.0);
 }
 // a/|a| when the length is already known (same sqrt value the reference recomputes)
 __device__ __forceinline__ d2 normalize_known(d2 a, double l) {
     if (l != 0)
-        return mk(a.x/l, a.y/l);
+        return mk(ddiv(a.x, l), ddiv(a.y, l));
     return mk(0, 1.0);
 }
 // mix(a, b, w) = (1-w)*a + w*b
@@ -325,18 +338,18 @@ __device__ __forceinline__ Roots solve_quadratic(double a, double b, double c) {
             r.n = c == 0 ? -1 : 0;
             return r;
         }
-        r.t0 = -c/b;
+        r.t0 = ddiv(-c, b);
         r.n = 1;
         return r;
     }
     double dscr = b*b-4*a*c;
     if (dscr > 0) {
-        dscr = sqrt(dscr);
-        r.t0 = (-b+dscr)/(2*a);
-        r.t1 = (-b-dscr)/(2*a);
+        dscr = dsqrt(dscr);
+        r.t0 = ddiv(-b+dscr, 2*a);
+        r.t1 = ddiv(-b-dscr, 2*a);
         r.n = 2;
     } else if (dscr == 0) {
-        r.t0 = -b/(2*a);
+        r.t0 = ddiv(-b, 2*a);
         r.n = 1;
     }
     return r;
@@ -900,51 +913,12 @@ __device__ __forceinline__ void load_selector(ContourStore &st, int c, Sel<MODE>
     }
 }
 
-// ShapeDistanceFinder<Combiner<Selector>>::oneShotDistance at point p over the glyph's records [0, nRec).
-// recs is shared memory (small glyphs) or the global prepared buffer (big shapes); every thread of the CTA walks the same
-// record at the same time, so loads broadcast.  out gets NOUT raw (unmapped) fp64 distances.
-template <int MODE, bool OVERLAP, typename IT>
-__device__ __forceinline__ void shape_distance_over(const SegRec *recs, int nRec, IT it, d2 p, ContourStore store, double *out) {
+// OverlappingContourCombiner::distance (contour-combiners.cpp:78-134) over the nc parked contours of `store`.
+template <int MODE>
+__device__ __forceinline__ void combine_overlapping(const SegRec *recs, d2 p, ContourStore store, int nc, double *out) {
     const int NOUT = ModeTraits<MODE>::NOUT;
     typedef StoreLayout<MODE> L;
-    if (!OVERLAP) {
-        Sel<MODE> sel;
-        sel_init(sel);
-        double cap[ModeTraits<MODE>::NCH];
-        distance_caps<MODE>(recs, it, 0, nRec-1, p, cap);
-        for (int i = 0; i < nRec; ++i) {
-            const int j = it.at(i);
-            sel_add_edge<MODE>(sel, recs[j], j, p, cap);
-        }
-        sel_distance<MODE>(sel, recs, p, out);
-    } else {
-        // ---- walk the edges with ONE live selector; park each finished contour
-        int nc = 0;
-        {
-            Sel<MODE> cur;
-            sel_init(cur);
-            int j0 = 0;
-            while (j0 < nRec) {
-                // the contour's records are at positions [j0, j1] (SeqIter: its closing record carries SEG_LAST_IN_CONTOUR)
-                const int j1 = it.group_last(recs, j0, nRec);
-                double cap[ModeTraits<MODE>::NCH];
-                distance_caps<MODE>(recs, it, j0, j1, p, cap);
-                for (int i = j0; i <= j1; ++i) {
-                    const int j = it.at(i);
-                    sel_add_edge<MODE>(cur, recs[j], j, p, cap);
-                }
-                double cd[NOUT];
-                sel_distance<MODE>(cur, recs, p, cd);
-                store_selector<MODE>(store, nc, cur);
-                #pragma unroll
-                for (int k = 0; k < NOUT; ++k)
-                    store.at(nc, L::DIST+k) = cd[k];
-                store.at(nc, L::WINDING) = double(recs[it.at(j1)].winding);
-                sel_init(cur);
-                ++nc;
-                j0 = j1+1;
-            }
-        }
+    {
         // ---- OverlappingContourCombiner::distance (contour-combiners.cpp:78-134)
         double shapeD[NOUT], innerD[NOUT], outerD[NOUT], dist[NOUT];
         {
@@ -1012,6 +986,55 @@ __device__ __forceinline__ void shape_distance_over(const SegRec *recs, int nRec
         }
         #pragma unroll
         for (int k = 0; k < NOUT; ++k) out[k] = dist[k];
+    }
+}
+
+// ShapeDistanceFinder<Combiner<Selector>>::oneShotDistance at point p over the glyph's records [0, nRec).
+// recs is shared memory (small glyphs) or the global prepared buffer (big shapes); every thread of the CTA walks the same
+// record at the same time, so loads broadcast.  out gets NOUT raw (unmapped) fp64 distances.
+template <int MODE, bool OVERLAP, typename IT>
+__device__ __forceinline__ void shape_distance_over(const SegRec *recs, int nRec, IT it, d2 p, ContourStore store, double *out) {
+    const int NOUT = ModeTraits<MODE>::NOUT;
+    typedef StoreLayout<MODE> L;
+    if (!OVERLAP) {
+        Sel<MODE> sel;
+        sel_init(sel);
+        double cap[ModeTraits<MODE>::NCH];
+        distance_caps<MODE>(recs, it, 0, nRec-1, p, cap);
+        for (int i = 0; i < nRec; ++i) {
+            const int j = it.at(i);
+            sel_add_edge<MODE>(sel, recs[j], j, p, cap);
+        }
+        sel_distance<MODE>(sel, recs, p, out);
+    } else {
+        // ---- walk the edges with ONE live selector; park each finished contour
+        int nc = 0;
+        {
+            Sel<MODE> cur;
+            sel_init(cur);
+            int j0 = 0;
+            while (j0 < nRec) {
+                // the contour's records are at positions [j0, j1] (SeqIter: its closing record carries SEG_LAST_IN_CONTOUR)
+                const int j1 = it.group_last(recs, j0, nRec);
+                double cap[ModeTraits<MODE>::NCH];
+                distance_caps<MODE>(recs, it, j0, j1, p, cap);
+                for (int i = j0; i <= j1; ++i) {
+                    const int j = it.at(i);
+                    sel_add_edge<MODE>(cur, recs[j], j, p, cap);
+                }
+                double cd[NOUT];
+                sel_distance<MODE>(cur, recs, p, cd);
+                store_selector<MODE>(store, nc, cur);
+                #pragma unroll
+                for (int k = 0; k < NOUT; ++k)
+                    store.at(nc, L::DIST+k) = cd[k];
+                store.at(nc, L::WINDING) = double(recs[it.at(j1)].winding);
+                sel_init(cur);
+                ++nc;
+                j0 = j1+1;
+            }
+        }
+        combine_overlapping<MODE>(recs, p, store, nc, out);
     }
 }
 

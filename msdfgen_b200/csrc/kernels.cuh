@@ -16,6 +16,7 @@
 #pragma once
 
 #include "distance_core.cuh"
+#include "distance_filter.cuh"
 
 namespace b200 {
 
@@ -56,6 +57,8 @@ struct KernelParams {
     size_t listStride, listPerCta, capStride;   // list capacity; ints per CTA (list + group ends); cap slots per CTA
     double *scratch;              // per-thread contour-distance slices for many-contour shapes
     size_t scratchStride;         // = gridDim.x * CTA_THREADS
+    unsigned *filt;               // k1a -> k1b: per-unit filter words (distance_filter.cuh)
+    const unsigned long long *tileFilt;   // word offset of every small tile's first unit in filt
     // error correction config
     int ecMode, ecDcm;
     double minDeviationRatio, minImproveRatio;
@@ -235,6 +238,271 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
             unsigned nPix = tileEnd-passBase < CTA_THREADS ? tileEnd-passBase : CTA_THREADS;
             store_tile(P.field+s_g.outOffset+size_t(passBase)*NOUT, s_out, int(nPix)*NOUT);
             __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k1a_filter + k1b_exact — the distance kernels of glyphs whose records fit in shared memory (<= SMEM_RECORDS segments).
+//
+// Both are persistent 128-thread CTAs pulling 1024-texel tiles from an atomic counter.  Per glyph change one elected thread
+// TMA-copies the raw control points into shared memory and the CTA prepares what the kernel needs there: k1a the fp32 filter
+// records (FRec), k1b the SegRecs (fp64 constants of the exact evaluation).  Inside a tile there is NO CTA barrier: every warp
+// pulls 32-texel units from a shared-memory counter (8x4 texel blocks when the tile is a whole number of rows of a width that
+// is a multiple of 8 — neighbouring lanes then keep nearly the same edges —, 32x1 strips otherwise).
+//   k1a_filter  passes 1 and 2 of distance_filter.cuh: fp32, ~40 registers, a loop body that fits the L0 instruction cache;
+//               writes the unit's survivor / candidate masks and upper bounds (interleaved words, whole 128-byte lines).
+//   k1b_exact   pass 3 + contour combiner in fp64 for what the filter kept; stages its 32 texels in the warp's shared-memory
+//               slice and writes them back as float4 rows.
+#define K1_THREADS 128
+#define K1_WARPS (K1_THREADS/32)
+
+// Unit geometry of a tile (uniform across the CTA).
+struct UnitGrid {
+    bool blocked;
+    int row0, nRows, blocksAcross, nUnits;
+    unsigned pixEnd;
+    __device__ __forceinline__ UnitGrid(const GlyphDesc &g, const TileDesc &td) {
+        const int w = g.w;
+        const unsigned total = unsigned(w)*unsigned(g.h);
+        pixEnd = td.pix0+TILE_PIXELS < total ? td.pix0+TILE_PIXELS : total;
+        blocked = (w&7) == 0 && w <= TILE_PIXELS && (TILE_PIXELS%w) == 0;
+        row0 = blocked ? int(td.pix0/unsigned(w)) : 0;
+        nRows = blocked ? int((pixEnd-td.pix0)/unsigned(w)) : 0;
+        blocksAcross = w>>3;
+        nUnits = blocked ? blocksAcross*((nRows+3)>>2) : int((pixEnd-td.pix0+31u)>>5);
+    }
+    // texel of (unit, lane): returns validity; idle lanes shadow a texel of the unit (the exact walk votes warp-wide)
+    __device__ __forceinline__ bool texel(const GlyphDesc &g, const TileDesc &td, int u, unsigned lane, int &x, int &yOut) const {
+        bool valid;
+        if (blocked) {
+            const int bx = u%blocksAcross, by = u/blocksAcross;
+            x = bx*8+int(lane&7);
+            yOut = row0+by*4+int(lane>>3);
+            valid = yOut < row0+nRows;
+            if (!valid)
+                yOut = row0+nRows-1;
+        } else {
+            unsigned i = td.pix0+unsigned(u)*32u+lane;
+            valid = i < pixEnd;
+            if (!valid)
+                i = pixEnd-1;
+            x = int(i%unsigned(g.w));
+            yOut = int(i/unsigned(g.w));
+        }
+        return valid;
+    }
+};
+
+// Projection::unproject(Point2(x+.5, y+.5)) of output texel (x, yOut)
+__device__ __forceinline__ d2 texel_point(const GlyphDesc &g, int x, int yOut) {
+    const int y = g.flip ? g.h-1-yOut : yOut;
+    return mk(ddiv(g.x0+x+.5, g.sx)-g.tx, ddiv(g.y0+y+.5, g.sy)-g.ty);
+}
+
+// origin of the filter's local coordinates: the centre of the glyph's texel block in shape units
+__device__ __forceinline__ d2 filter_origin(const GlyphDesc &g) {
+    return mk((g.x0+.5*g.w)/g.sx-g.tx, (g.y0+.5*g.h)/g.sy-g.ty);
+}
+
+// group ends (positions after the last record of every non-empty contour) and filter words per texel; one thread
+template <int MODE, bool OVERLAP>
+__device__ __forceinline__ void build_groups(const KernelParams &P, const GlyphDesc &g, int *groupEnd, int *nGroups, unsigned *wordsPerTexel) {
+    int ng = 0;
+    unsigned words = 0;
+    for (unsigned c = g.c0; c < g.c1; ++c) {
+        const unsigned b = P.raw.cbegin[c], e = P.raw.cbegin[c+1];
+        if (e > b) {
+            groupEnd[ng++] = int(e-g.s0);
+            words += filter_words_group<MODE>(e-b);
+        }
+    }
+    if (!OVERLAP)
+        words = g.s1 > g.s0 ? filter_words_group<MODE>(g.s1-g.s0) : 0u;
+    *nGroups = ng;
+    *wordsPerTexel = words;
+}
+
+template <int MODE, bool OVERLAP>
+__global__ void __launch_bounds__(K1_THREADS, 8) k1a_filter(KernelParams P) {
+    __shared__ __align__(16) double s_points[SMEM_RECORDS*8];
+    __shared__ __align__(16) FRec s_frecs[SMEM_RECORDS];
+    __shared__ int s_groupEnd[SMEM_RECORDS];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ GlyphDesc s_g;
+    __shared__ float s_slack;
+    __shared__ int s_nGroups, s_tile, s_unit;
+    __shared__ unsigned s_words, s_extent;
+    unsigned phase = 0;
+    if (threadIdx.x == 0)
+        mbar_init(&s_mbar);
+    const unsigned lane = threadIdx.x&31;
+    int stagedGlyph = -1;
+    for (;;) {
+        __syncthreads();        // every warp has left the previous tile
+        if (threadIdx.x == 0) {
+            s_tile = P.tileBegin+atomicAdd(&P.counters[P.counterIndex], 1);
+            s_unit = 0;
+        }
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= P.tileEnd)
+            break;
+        const TileDesc td = P.tiles[tile];
+        if ((int) td.glyph != stagedGlyph) {
+            if (threadIdx.x == 0) {
+                s_g = P.glyphs[td.glyph];
+                s_extent = 0;
+            }
+            __syncthreads();
+            const unsigned n = s_g.s1-s_g.s0;
+            const d2 O = filter_origin(s_g);
+            if (n) {
+                if (threadIdx.x == 0)
+                    tma_load_1d(s_points, P.raw.points+8*size_t(s_g.s0), n*64u, &s_mbar);
+                mbar_wait(&s_mbar, phase);
+                phase ^= 1u;
+                // M: largest |local coordinate| of any control point
+                for (unsigned j = threadIdx.x; j < n; j += blockDim.x) {
+                    const int order = P.raw.orders[s_g.s0+j];
+                    double m = 0;
+                    for (int i = 0; i <= order; ++i)
+                        m = fmax(m, fmax(fabs(s_points[8*j+2*i]-O.x), fabs(s_points[8*j+2*i+1]-O.y)));
+                    atomicMax(&s_extent, __float_as_uint(m == m ? float_up(m) : __int_as_float(0x7f800000)));
+                }
+            }
+            if (threadIdx.x == 0)
+                build_groups<MODE, OVERLAP>(P, s_g, s_groupEnd, &s_nGroups, &s_words);
+            __syncthreads();
+            float M = __uint_as_float(s_extent);
+            M = fmaxf(M, float_up((.5*s_g.w+1)/fabs(s_g.sx)));
+            M = fmaxf(M, float_up((.5*s_g.h+1)/fabs(s_g.sy)));
+            const float slack = M*1.52587890625e-5f+float_up(fmax(fabs(O.x), fabs(O.y)))*5.7e-14f+1e-37f;       // 2^-16 M + 2^-44 |O|
+            if (threadIdx.x == 0)
+                s_slack = slack;
+            RawShapes rs = P.raw;
+            rs.points = s_points-8*size_t(s_g.s0);          // prepare_record indexes segments by their global index
+            for (unsigned j = threadIdx.x; j < n; j += blockDim.x) {
+                SegRec tmp;
+                prepare_record(rs, s_g, j, tmp);
+                make_filter_record<MODE>(tmp, O, slack, s_frecs[j]);
+            }
+            stagedGlyph = (int) td.glyph;
+            __syncthreads();
+        }
+        const UnitGrid grid(s_g, td);
+        const int nRec = int(s_g.s1-s_g.s0);
+        const d2 O = filter_origin(s_g);
+        unsigned *const tileWords = P.filt+P.tileFilt[tile];
+        const unsigned words = s_words;
+        for (;;) {
+            int u = 0;
+            if (lane == 0)
+                u = atomicAdd(&s_unit, 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= grid.nUnits)
+                break;
+            int x, yOut;
+            grid.texel(s_g, td, u, lane, x, yOut);
+            const d2 p = texel_point(s_g, x, yOut);
+            filter_texel<MODE, OVERLAP>(s_frecs, nRec, s_groupEnd, s_nGroups, s_slack, float(p.x-O.x), float(p.y-O.y),
+                                        tileWords+size_t(u)*words*32u+lane);
+        }
+    }
+}
+
+#ifndef K1B_MIN_CTAS
+#define K1B_MIN_CTAS 4
+#endif
+template <int MODE, bool OVERLAP>
+__global__ void __launch_bounds__(K1_THREADS, K1B_MIN_CTAS) k1b_exact(KernelParams P) {
+    const int NOUT = ModeTraits<MODE>::NOUT;
+    __shared__ SegRec s_recs[SMEM_RECORDS];
+    __shared__ __align__(16) double s_points[SMEM_RECORDS*8];
+    __shared__ int s_groupEnd[SMEM_RECORDS];
+    __shared__ __align__(16) float s_out[K1_WARPS][32*NOUT];
+    __shared__ __align__(8) unsigned long long s_mbar;
+    __shared__ GlyphDesc s_g;
+    __shared__ int s_nGroups, s_tile, s_unit;
+    __shared__ unsigned s_words;
+    unsigned phase = 0;
+    if (threadIdx.x == 0)
+        mbar_init(&s_mbar);
+    double localStore[OVERLAP ? B200_LOCAL_CONTOURS*StoreLayout<MODE>::PER_CONTOUR : 1];
+    const unsigned lane = threadIdx.x&31, warp = threadIdx.x>>5;
+    int stagedGlyph = -1;
+    for (;;) {
+        __syncthreads();        // every warp has left the previous tile
+        if (threadIdx.x == 0) {
+            s_tile = P.tileBegin+atomicAdd(&P.counters[P.counterIndex], 1);
+            s_unit = 0;
+        }
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= P.tileEnd)
+            break;
+        const TileDesc td = P.tiles[tile];
+        if ((int) td.glyph != stagedGlyph) {
+            if (threadIdx.x == 0)
+                s_g = P.glyphs[td.glyph];
+            __syncthreads();
+            stage_glyph(P, s_g, s_recs, s_points, &s_mbar, phase);
+            if (threadIdx.x == 0)
+                build_groups<MODE, OVERLAP>(P, s_g, s_groupEnd, &s_nGroups, &s_words);
+            stagedGlyph = (int) td.glyph;
+            __syncthreads();
+        }
+        const UnitGrid grid(s_g, td);
+        const int w = s_g.w;
+        const int nRec = int(s_g.s1-s_g.s0);
+        ContourStore store;
+        store.perContour = StoreLayout<MODE>::PER_CONTOUR;
+        if (OVERLAP && s_g.nonEmptyContours > B200_LOCAL_CONTOURS) {
+            store.base = P.scratch+(size_t(blockIdx.x)*K1_THREADS+threadIdx.x);
+            store.stride = P.scratchStride;
+        } else {
+            store.base = localStore;
+            store.stride = 1;
+        }
+        float *const tileOut = P.field+s_g.outOffset;
+        const unsigned *const tileWords = P.filt+P.tileFilt[tile];
+        const unsigned words = s_words;
+        for (;;) {
+            int u = 0;
+            if (lane == 0)
+                u = atomicAdd(&s_unit, 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= grid.nUnits)
+                break;
+            int x, yOut;
+            const bool valid = grid.texel(s_g, td, u, lane, x, yOut);
+            const d2 p = texel_point(s_g, x, yOut);
+            double dist[NOUT];
+            exact_texel<MODE, OVERLAP>(s_recs, nRec, s_groupEnd, s_nGroups, tileWords+size_t(u)*words*32u+lane, p, store, dist);
+            if (valid) {
+                #pragma unroll
+                for (int k = 0; k < NOUT; ++k)
+                    s_out[warp][lane*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));      // DistanceMapping::operator()
+            }
+            __syncwarp();
+            if (grid.blocked) {
+                // 4 rows of 8 texels: 2*NOUT float4 per row, rows contiguous in the warp's slice
+                const int by = u/grid.blocksAcross, bx = u%grid.blocksAcross;
+                const int r = int(lane)/(2*NOUT), q = int(lane)%(2*NOUT);
+                if (r < 4 && by*4+r < grid.nRows) {
+                    float4 *dst = reinterpret_cast<float4 *>(tileOut+(size_t(grid.row0+by*4+r)*w+bx*8)*NOUT)+q;
+                    *dst = reinterpret_cast<const float4 *>(s_out[warp])[lane];
+                }
+            } else {
+                const unsigned i0 = td.pix0+unsigned(u)*32u;
+                const int nFloats = int((grid.pixEnd-i0 < 32u ? grid.pixEnd-i0 : 32u))*NOUT;
+                float *dst = tileOut+size_t(i0)*NOUT;
+                for (int i = int(lane); i < (nFloats>>2); i += 32)
+                    reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(s_out[warp])[i];
+                for (int i = (nFloats&~3)+int(lane); i < nFloats; i += 32)
+                    dst[i] = s_out[warp][i];
+            }
+            __syncwarp();
         }
     }
 }
