@@ -115,6 +115,7 @@ struct b200msdf_batch {
     DevBuf blocks, blockWork;     // big shapes: 2-D block tiles of k1_big_blocks and its per-CTA list / cap workspace
     int nBlocks = 0, maxBigSegs = 0, maxBigContours = 0;
     std::vector<TileDesc> hBlocks;
+    DevBuf k1Counters;            // one tile counter per k1a / k1b launch of a round
     DevBuf filt, tileFilt;        // k1a -> k1b filter words (sized at launch) and the small tiles' word offsets: [overlap][tile], [simple][tile]
     size_t filtWords[2] = { 0, 0 };
     std::vector<unsigned long long> hTileFilt;
@@ -125,7 +126,7 @@ struct b200msdf_batch {
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
         bigGlyphs.release(); bigRecs.release(); bigCull.release(); bigPerp.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); bytes.release(); byteTargets.release(); signMatch.release();
-        blocks.release(); blockWork.release(); filt.release(); tileFilt.release();
+        blocks.release(); blockWork.release(); filt.release(); tileFilt.release(); k1Counters.release();
     }
 };
 
@@ -453,16 +454,44 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
     if (getenv("B200MSDF_K1_LEGACY")) {
         if ((rc = launch_tiles(ctx, k1_distance_field<MODE, OVERLAP, false>, P, scratch))) return rc;
     } else if (P.nSmallTiles > 0) {
-        // k1a_filter (fp32 bounds -> survivor masks) then k1b_exact (fp64 evaluation of the survivors + contour combiner)
+        // k1a_filter (fp32 bounds -> survivor masks) then k1b_exact (fp64 evaluation of the survivors + contour combiner).
+        // B200MSDF_K1_ROUND=n runs them in rounds of n tiles that reuse one filter-word buffer (L2-resident words, less memory);
+        // measured on B200: the tail of every persistent launch costs more than the L2 hits save (4096-glyph atlas: one round
+        // 2.58 ms, 2048 tiles 2.75, 1024 tiles 2.99), so the default is ONE round up to 1 GiB of filter words
         b200msdf_batch *bb = ctx->cur;
-        const size_t words = bb->filtWords[OVERLAP ? 0 : 1];
-        if ((rc = bb->filt.reserve(words*sizeof(unsigned)+256))) return rc;
-        P.filt = bb->filt.as<unsigned>();
+        const unsigned long long *hOff = bb->hTileFilt.data()+(OVERLAP ? 0 : (size_t) P.nSmallTiles);
+        const size_t totalWords = bb->filtWords[OVERLAP ? 0 : 1];
         P.tileFilt = bb->tileFilt.as<unsigned long long>()+(OVERLAP ? 0 : (size_t) P.nSmallTiles);
-        P.counterIndex = 5;
-        if ((rc = launch_tiles(ctx, k1a_filter<MODE, OVERLAP>, P, 0, 0, K1_THREADS))) return rc;
-        P.counterIndex = 0;
-        if ((rc = launch_tiles(ctx, k1b_exact<MODE, OVERLAP>, P, scratch, 0, K1_THREADS))) return rc;
+        int roundTiles = P.nSmallTiles;
+        if (totalWords > (size_t) 256*1024*1024)
+            roundTiles = (int) ((double) P.nSmallTiles*(256.0*1024*1024)/(double) totalWords)+1;
+        if (const char *env = getenv("B200MSDF_K1_ROUND"))
+            roundTiles = atoi(env) > 0 ? atoi(env) : P.nSmallTiles;
+        const int rounds = (P.nSmallTiles+roundTiles-1)/roundTiles;
+        // every round reuses the same buffer (its lines then never leave the L2): sized for the largest round
+        size_t roundWords = 0;
+        for (int r = 0; r < rounds; ++r) {
+            const size_t t0 = (size_t) r*roundTiles, t1 = t0+roundTiles < (size_t) P.nSmallTiles ? t0+roundTiles : (size_t) P.nSmallTiles;
+            const size_t w = (t1 < (size_t) P.nSmallTiles ? hOff[t1] : totalWords)-hOff[t0];
+            if (w > roundWords) roundWords = w;
+        }
+        if ((rc = bb->filt.reserve(roundWords*sizeof(unsigned)+256))) return rc;
+        if ((rc = bb->k1Counters.reserve(sizeof(int)*2*(size_t) rounds))) return rc;
+        CUDA_TRY(cudaMemsetAsync(bb->k1Counters.p, 0, sizeof(int)*2*(size_t) rounds, ctx->stream));
+        int *const batchCounters = P.counters;
+        P.counters = bb->k1Counters.as<int>();
+        for (int r = 0; r < rounds && !rc; ++r) {
+            P.tileBegin = r*roundTiles;
+            P.tileEnd = P.tileBegin+roundTiles < P.nSmallTiles ? P.tileBegin+roundTiles : P.nSmallTiles;
+            P.counterIndex = 2*r;
+            P.filt = bb->filt.as<unsigned>()-hOff[P.tileBegin];       // tileFilt offsets are batch-wide; the round starts at 0
+            rc = launch_tiles(ctx, k1a_filter<MODE, OVERLAP>, P, 0, 0, K1_THREADS);
+            P.counterIndex = 2*r+1;
+            if (!rc) rc = launch_tiles(ctx, k1b_exact<MODE, OVERLAP>, P, scratch, 0, K1_THREADS);
+        }
+        P.counters = batchCounters;
+        P.tileBegin = 0; P.tileEnd = P.nSmallTiles; P.counterIndex = 0;
+        if (rc) return rc;
     }
     // big shapes: 2-D blocks with per-block record lists; each resident CTA owns a slice of the list / cap workspace
     b200msdf_batch *b = ctx->cur;

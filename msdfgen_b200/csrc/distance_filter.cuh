@@ -169,17 +169,20 @@ __device__ __forceinline__ void filter_texel(const FRec *frecs, int nRec, const 
                 const float qx = __fmaf_rn(-t, c.z, apx), qy = __fmaf_rn(-t, c.w, apy);
                 const float d2f = __fmaf_rn(qx, qx, qy*qy);
                 const float thr = Um+m.y;
-                if (!(d2f > thr*thr*1.00001f))
+                const bool keep = !(d2f > thr*thr*1.00001f);
+                if (keep)
                     surv |= bit;
-                else if (MODE != 1) {
+                if (MODE != 1) {
                     const float4 dir = reinterpret_cast<const float4 *>(frecs+j)[1];
                     const float4 bis = reinterpret_cast<const float4 *>(frecs+j)[2];
-                    const float lim = Um+slack;
-                    // A: |cross(ap, aDir)| <= U, dot(ap, aBis) > 0, -dot(ap, aDir) > 0
+                    // |pd| limit: a dropped edge's candidate matters only below U; a survivor's is accepted by the reference iff
+                    // |pd| < |d(edge)|, and |d(edge)| <= chord distance + deviation (no such bound for the cubic Newton search)
+                    const float lim = (keep ? ((mask&FREC_CUBIC) ? 3.0e38f : __fmaf_rn(sqrt_approx(d2f), 1.000004f, m.y)) : Um)+slack;
+                    // A: cross(ap, aDir), dot(ap, aBis) > 0, -dot(ap, aDir) > 0
                     const float pdA = __fmaf_rn(apx, dir.y, -apy*dir.x);
                     if (!(fabsf(pdA) > lim) && !(__fmaf_rn(apx, bis.x, apy*bis.y) < -slack) && !(__fmaf_rn(apx, dir.x, apy*dir.y) > slack))
                         candA |= bit;
-                    // B: |cross(bp, bDir)| <= U, -dot(bp, bBis) > 0, dot(bp, bDir) > 0
+                    // B: cross(bp, bDir), -dot(bp, bBis) > 0, dot(bp, bDir) > 0
                     const float bpx = apx-c.z, bpy = apy-c.w;
                     const float pdB = __fmaf_rn(bpx, dir.w, -bpy*dir.z);
                     if (!(fabsf(pdB) > lim) && !(__fmaf_rn(bpx, bis.z, bpy*bis.w) > slack) && !(__fmaf_rn(bpx, dir.z, bpy*dir.w) < -slack))
@@ -385,21 +388,46 @@ __device__ __forceinline__ void exact_texel(const SegRec *recs, int nRec, const 
     sel_init(cur);
     int nc = 0;
     int j0 = 0;
+    // The words of the NEXT contour (bounds + first round of masks) are requested while the current one is evaluated.
+    const int WPR = MODE == 1 ? 1 : 3;          // words per round
+    unsigned nU[NCH], nS = 0, nA = 0, nB = 0;
+    if (nGroups > 0) {
+        #pragma unroll
+        for (int k = 0; k < NCH; ++k)
+            nU[k] = __ldcs(in+32*k);
+        nS = __ldcs(in+32*NCH);
+        if (MODE != 1) {
+            nA = __ldcs(in+32*(NCH+1));
+            nB = __ldcs(in+32*(NCH+2));
+        }
+    }
     for (int g = 0; g < nGroups; ++g) {
         const int jEnd = OVERLAP ? groupEnd[g] : nRec;
         float U[NCH];
         #pragma unroll
-        for (int k = 0; k < NCH; ++k) {
-            U[k] = __uint_as_float(__ldcs(in));
-            in += 32;
+        for (int k = 0; k < NCH; ++k)
+            U[k] = __uint_as_float(nU[k]);
+        unsigned surv = nS, candA = nA, candB = nB;
+        const unsigned *more = in+32*(NCH+WPR);                     // this contour's further rounds
+        in += 32*(NCH+WPR*((jEnd-j0+31)>>5));                        // the next contour's words
+        if (g+1 < nGroups) {
+            #pragma unroll
+            for (int k = 0; k < NCH; ++k)
+                nU[k] = __ldcs(in+32*k);
+            nS = __ldcs(in+32*NCH);
+            if (MODE != 1) {
+                nA = __ldcs(in+32*(NCH+1));
+                nB = __ldcs(in+32*(NCH+2));
+            }
         }
         for (int c0 = j0; c0 < jEnd; c0 += 32) {
-            unsigned surv = __ldcs(in), candA = 0, candB = 0;
-            in += 32;
-            if (MODE != 1) {
-                candA = __ldcs(in);
-                candB = __ldcs(in+32);
-                in += 64;
+            if (c0 != j0) {
+                surv = __ldcs(more);
+                if (MODE != 1) {
+                    candA = __ldcs(more+32);
+                    candB = __ldcs(more+64);
+                }
+                more += 32*WPR;
             }
             // ---- pass 3a: survivors, exactly as the reference (edge-selectors.cpp:129-160 / 174-227).  Record-major over the
             // union of the warp's survivors: the record, hence the segment type, is uniform across the warp and its loads
@@ -430,7 +458,7 @@ __device__ __forceinline__ void exact_texel(const SegRec *recs, int nRec, const 
                                 cur.ch[k].d = r.d; cur.ch[k].dot = r.dot; cur.ch[k].near = near;
                             }
                 }
-                if (MODE != 1) {
+                if (MODE != 1 && ((candA>>b)&1u)) {
                     const d2 ap = p-s.p0;
                     const double pdA = cross(ap, s.aDir);
                     if (dot(ap, s.aBis) > 0 && -dot(ap, s.aDir) > 0 && fabs(pdA) < fabs(r.d)) {
@@ -439,6 +467,8 @@ __device__ __forceinline__ void exact_texel(const SegRec *recs, int nRec, const 
                             if (mask&(1<<k))
                                 chan_add_perp(cur.ch[k], pdA);
                     }
+                }
+                if (MODE != 1 && ((candB>>b)&1u)) {
                     const d2 bp = p-s.pEnd;
                     const double pdB = cross(bp, s.bDir);
                     if (-dot(bp, s.bBis) > 0 && dot(bp, s.bDir) > 0 && fabs(pdB) < fabs(r.d)) {
@@ -451,6 +481,8 @@ __device__ __forceinline__ void exact_texel(const SegRec *recs, int nRec, const 
             }
             // ---- pass 3b: perpendicular candidates of dropped edges
             if (MODE != 1) {
+                candA &= ~surv;         // (the survivors' candidates were handled with their exact distances above)
+                candB &= ~surv;
                 unsigned candAny = __reduce_or_sync(0xffffffffu, candA|candB);
                 while (candAny) {
                     const int b = __ffs(candAny)-1;

@@ -34,12 +34,6 @@ namespace b200 {
 #define CLS_CANDIDATE 1
 #define CLS_ARTIFACT 2
 #define EC_WARPS (CTA_THREADS/32)
-// Warp-level compaction of k2's out-of-line artifact tests (on; -DB200_K2_COMPACT=0 restores the per-lane walk): only ~10 of
-// 32 lanes have such tests, so the lanes first ENUMERATE them into a per-warp queue and the warp then runs 32 at a time.
-// Same tests with the same operands, so the same flags; measured 2.07 -> 1.91 ms for k2+k3 on the headline atlas.
-#ifndef B200_K2_COMPACT
-#define B200_K2_COMPACT 1
-#endif
 
 // mix<float, double>(a, b, t)
 __device__ __forceinline__ float mixf(float a, float b, double t) { return float((1.0-t)*a+t*b); }
@@ -91,22 +85,23 @@ struct TexelState {
     d2 shapeCoord, sdfCoord;
     const float *msd;
     unsigned texel;
-#if B200_K2_COMPACT
-    // the neighbour walk only ENUMERATES the tests that survive the prefilters (owner lane, kind, neighbour, channel pair packed
-    // in 16 bits) into a per-warp queue; the warp then runs 32 queued tests at a time
+    // k2 (SINK 0): the neighbour walk only ENUMERATES the tests that survive the prefilters (owner texel, kind, neighbour,
+    // channel pair packed in 16 bits) into a queue shared by the tile; the CTA then runs them 256 at a time
     unsigned short *queue;
     int *queueCount;
-    int lane;
-#endif
+    int tileTexel;
 };
 
-#if B200_K2_COMPACT
-#define K2_QUEUE (32*24)        // at most 8 neighbours x 3 channel pairs per texel
-__device__ __forceinline__ void enqueue_test(TexelState &k, int kind, int n, int pr) {
+// Tile-wide queue of out-of-line tests: texel index inside the tile (10 bits), kind (bit 10), neighbour (bits 11-12), channel pair
+// (bits 13-14).  A full queue makes the enqueuing lane run its test in place.
+#define K2_QUEUE 6144
+__device__ __forceinline__ bool enqueue_test(TexelState &k, int kind, int n, int pr) {
     int at = atomicAdd(k.queueCount, 1);
-    k.queue[at] = (unsigned short) (k.lane|(kind<<5)|(n<<6)|(pr<<8));
+    if (at >= K2_QUEUE)
+        return false;
+    k.queue[at] = (unsigned short) (k.tileTexel|(kind<<10)|(n<<11)|(pr<<13));
+    return true;
 }
-#endif
 
 // BaseArtifactClassifier::rangeTest (:30-41)
 __device__ __forceinline__ int range_test(bool protectedFlag, double span, double at, double bt, double xt, float am, float bm, float xm) {
@@ -295,10 +290,8 @@ __device__ __forceinline__ void find_errors_texel(const EcCtx<N> &e, TexelState 
             // is skipped without changing a result.
             float dA = a1-a0, dB = b1-b0;
             if ((dA > 0 && dB < 0) || (dA < 0 && dB > 0))
-#if B200_K2_COMPACT
-                if (SINK == 0) enqueue_test(k, 0, n, pr); else
-#endif
-                linear_artifact_inner<N, SINK, OVERLAP>(e, k, am, bm, a, b, dA, dB);
+                if (SINK != 0 || !enqueue_test(k, 0, n, pr))
+                    linear_artifact_inner<N, SINK, OVERLAP>(e, k, am, bm, a, b, dA, dB);
         }
     }
     // diagonally adjacent texels: hasDiagonalArtifact (:349-381) with b = horizontal, c = vertical neighbour
@@ -344,16 +337,13 @@ __device__ __forceinline__ void find_errors_texel(const EcCtx<N> &e, TexelState 
             // inside), and a non-negative discriminant (the very expression solveQuadratic evaluates)
             const bool vertexInside = (qa > 0 && qb < 0 && -qb < 2*qa && qc >= 0) || (qa < 0 && qb > 0 && qb < -2*qa && qc <= 0);
             if (signChange || (vertexInside && qb*qb-4*qa*qc >= 0))
-#if B200_K2_COMPACT
-                if (SINK == 0) enqueue_test(k, 1, n, pr); else
-#endif
-                diagonal_artifact_inner<N, SINK, OVERLAP>(e, k, am, dm, a, l, q, dA, dBC, dD, i0, i1, extremes);
+                if (SINK != 0 || !enqueue_test(k, 1, n, pr))
+                    diagonal_artifact_inner<N, SINK, OVERLAP>(e, k, am, dm, a, l, q, dA, dBC, dD, i0, i1, extremes);
         }
     }
 }
 
-#if B200_K2_COMPACT
-// One queued test (B200_K2_COMPACT): rebuilds exactly the operands find_errors_texel had at the enqueue site for texel
+// One queued test: rebuilds exactly the operands find_errors_texel had at the enqueue site for texel
 // (x, y), neighbour n and channel pair pr, and runs the out-of-line test.  k carries the owner's protection flags in and the
 // verdict bits out.
 template <int N>
@@ -399,7 +389,6 @@ __device__ __forceinline__ void run_queued_test(const EcCtx<N> &e, TexelState &k
     }
     #undef B200_PICK
 }
-#endif
 
 // edgeBetweenTexelsChannel (:154-169)
 __device__ __forceinline__ bool edge_between_channel(float a0, float a1, float a2, float b0, float b1, float b2, int ch) {
@@ -500,9 +489,12 @@ __device__ __forceinline__ EcSpans ec_spans(const GlyphDesc &g, double minDeviat
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k2: classification + apply.  The CTA stages the glyph's colour corners once per tile; after that its warps are
-// independent and pull 32-texel chunks of the tile from a shared-memory counter (work per texel varies by orders of
-// magnitude between texels near an edge and the rest).
+// k2: classification + apply, three phases per 1024-texel tile (two CTA barriers):
+//   1  every warp pulls 32-texel chunks (8x4 blocks where the tile allows): protection flags per texel into shared memory, and
+//      the neighbour walk of both findErrors passes, which only ENUMERATES the out-of-line tests (the ones with fp64 divisions,
+//      square roots, interpolations) that survive the exact prefilters into a tile-wide queue — about 0.4 per texel;
+//   2  the whole CTA runs the queued tests, 256 at a time with every lane busy, and ORs the verdicts into the owners' flags;
+//   3  apply (error texels <- median), stencil and the float4 write-back.
 template <int N>
 __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
     __shared__ int2 s_corner[SMEM_RECORDS];
@@ -510,11 +502,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
     __shared__ GlyphDesc s_g;
     __shared__ int s_tile;
     __shared__ int s_chunk;
-#if B200_K2_COMPACT
-    __shared__ unsigned short s_queue[EC_WARPS][K2_QUEUE];
-    __shared__ int s_queueCount[EC_WARPS];
-    __shared__ int s_verdict[EC_WARPS][32];      // per owner lane: bit 0 protBase, 1 protShape (in); 2 errBase, 3 errShape, 4 overflow (out)
-#endif
+    __shared__ unsigned short s_queue[K2_QUEUE];
+    __shared__ int s_queueCount;
+    __shared__ int s_state[TILE_PIXELS];         // per texel of the tile: bit 0 protBase, 1 protShape; 2 errBase, 3 errShape, 4 overflow
 
     const int warp = threadIdx.x>>5, lane = threadIdx.x&31;
     int stagedGlyph = -1;
@@ -526,6 +516,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
         if (threadIdx.x == 0) {
             s_tile = P.tileBegin+atomicAdd(&P.counters[P.counterIndex], 1);
             s_chunk = 0;
+            s_queueCount = 0;
         }
         __syncthreads();
         int tile = s_tile;
@@ -560,6 +551,29 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
         e.recs = nullptr; e.nRec = 0;
         const EcSpans sp = ec_spans(s_g, P.minDeviationRatio);
 
+        // ---- phase 0: protectCorners (:121-151) as a scatter — every colour corner marks its 2x2 texels (bit 0 of the state)
+        for (unsigned t = threadIdx.x; t < TILE_PIXELS; t += blockDim.x)
+            s_state[t] = 0;
+        __syncthreads();
+        if (P.ecMode == 2 && needCorners) {
+            for (int j = threadIdx.x; j < nRec; j += blockDim.x) {
+                int cl, cb;
+                if (bigRecs) { cl = bigRecs[j].cornerL; cb = bigRecs[j].cornerB; }
+                else { int2 c = s_corner[j]; cl = c.x; cb = c.y; }
+                #pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const int x = cl+(d&1), y = cb+(d>>1);
+                    if (x >= 0 && y >= 0 && x < w && y < h) {
+                        const unsigned i = unsigned(s_g.flip ? h-1-y : y)*unsigned(w)+unsigned(x);
+                        if (i >= td.pix0 && i < tileEnd)
+                            atomicOr(&s_state[i-td.pix0], 1);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- phase 1: protection + enumeration
         for (;;) {
             int chunk = 0;
             if (lane == 0)
@@ -571,153 +585,83 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
             unsigned i = chunkBase+lane;
             // 8x4 texel blocks instead of 32x1 strips when the tile is a whole number of 4-row groups: lanes of a warp then
             // share most of their 3x3 neighbourhoods (cache lines) and take more similar branches
-            unsigned blockOrigin = 0;
             if (blocked) {
                 const unsigned blocksAcross = unsigned(w)>>3;
                 unsigned bx = unsigned(chunk)%blocksAcross, by = unsigned(chunk)/blocksAcross;
-                blockOrigin = td.pix0+by*4u*unsigned(w)+bx*8u;
-                i = blockOrigin+unsigned(lane>>3)*unsigned(w)+unsigned(lane&7);
+                i = td.pix0+by*4u*unsigned(w)+bx*8u+unsigned(lane>>3)*unsigned(w)+unsigned(lane&7);
             }
-#if B200_K2_COMPACT
-            if (lane == 0)
-                s_queueCount[warp] = 0;
-            __syncwarp();
-            int x = 0, y = 0, flags = 0;
-            TexelState k;
             if (i < tileEnd) {
-                x = int(i%unsigned(w));
-                int yOut = int(i/unsigned(w));
-                y = s_g.flip ? h-1-yOut : yOut;
+                const int x = int(i%unsigned(w));
+                const int yOut = int(i/unsigned(w));
+                const int y = s_g.flip ? h-1-yOut : yOut;
+                bool prot = (s_state[i-td.pix0]&1) != 0;
                 // msdfErrorCorrectionInner: protection stage
                 if (P.ecMode == 2) {
-                    bool prot = false;
-                    if (needCorners)
-                        for (int j = 0; j < nRec; ++j) {
-                            int cl, cb;
-                            if (bigRecs) { cl = bigRecs[j].cornerL; cb = bigRecs[j].cornerB; }
-                            else { int2 c = s_corner[j]; cl = c.x; cb = c.y; }
-                            if (unsigned(x-cl) <= 1u && unsigned(y-cb) <= 1u)
-                                prot = true;
-                        }
                     if (!prot)
                         prot = protect_edges_texel<N>(e.f, x, y, sp.hRadius, sp.vRadius, sp.dRadius);
-                    if (prot)
-                        flags |= EC_FLAG_PROTECTED;
                 } else if (P.ecMode == 3)
-                    flags |= EC_FLAG_PROTECTED;
-                // detection stage: both passes in one walk
-                k.useBase = useBase;
-                k.protBase = (flags&EC_FLAG_PROTECTED) != 0;
-                k.useShape = useShape;
-                // protectAll() runs between the two passes when distanceCheckMode == CHECK_DISTANCE_AT_EDGE
-                k.protShape = k.protBase || (useBase && P.ecDcm == 1);
-                k.errBase = k.errShape = k.overflow = false;
-                k.texel = i;
-                k.queue = s_queue[warp];
-                k.queueCount = &s_queueCount[warp];
-                k.lane = lane;
-                s_verdict[warp][lane] = (k.protBase ? 1 : 0)|(k.protShape ? 2 : 0);
-                find_errors_texel<N, 0, false>(e, k, x, y, sp.hSpan, sp.vSpan, sp.dSpan);     // SINK 0: enumerates
-            }
-            __syncwarp();
-            // the warp runs the queued tests 32 at a time; verdicts go back to the owners through shared memory
-            {
-                const int nQueued = s_queueCount[warp];
-                for (int base = 0; base < nQueued; base += 32) {
-                    const int q = base+lane;
-                    if (q < nQueued) {
-                        const unsigned item = s_queue[warp][q];
-                        const int owner = int(item&31u), kind = int((item>>5)&1u), n = int((item>>6)&3u), pr = int((item>>8)&3u);
-                        const unsigned io = blocked ? blockOrigin+unsigned(owner>>3)*unsigned(w)+unsigned(owner&7) : chunkBase+unsigned(owner);
-                        const int ox = int(io%unsigned(w));
-                        const int oyOut = int(io/unsigned(w));
-                        const int oy = s_g.flip ? h-1-oyOut : oyOut;
-                        const int state = *(volatile int *) &s_verdict[warp][owner];
-                        TexelState t;
-                        t.useBase = useBase; t.useShape = useShape;
-                        t.protBase = (state&1) != 0; t.protShape = (state&2) != 0;
-                        // an owner already found in error needs no exact-distance candidates (classify_point's short cut)
-                        const bool knownError = (state&12) != 0;
-                        t.errBase = knownError; t.errShape = false; t.overflow = false;
-                        t.texel = io;
-                        t.queue = nullptr; t.queueCount = nullptr; t.lane = owner;
-                        run_queued_test<N>(e, t, ox, oy, kind, n, pr, sp.hSpan, sp.vSpan, sp.dSpan);
-                        const int bits = ((t.errBase && !knownError) ? 4 : 0)|(t.errShape ? 8 : 0)|(t.overflow ? 16 : 0);
-                        if (bits)
-                            atomicOr(&s_verdict[warp][owner], bits);
-                    }
-                }
-            }
-            __syncwarp();
-            if (i < tileEnd) {
-                {
-                    const int state = s_verdict[warp][lane];
-                    k.errBase = (state&4) != 0;
-                    k.errShape = (state&8) != 0;
-                    k.overflow = (state&16) != 0;
-                }
-                if (k.errBase || k.errShape)
-                    flags |= EC_FLAG_ERROR;
-                if (k.protShape && useShape)
-                    flags |= EC_FLAG_PROTECTED;
-                if (k.overflow && !(flags&EC_FLAG_ERROR))
-                    flags |= EC_FLAG_RECHECK;
-                // apply (:459-479)
-                const float *c = e.f.at(x, y);
-                float o0 = c[0], o1 = c[1], o2 = c[2];
-                if (flags&EC_FLAG_ERROR) {
-                    float m = median3f(o0, o1, o2);
-                    o0 = m; o1 = m; o2 = m;
-                }
-                s_out[warp][lane*N+0] = o0;
-                s_out[warp][lane*N+1] = o1;
-                s_out[warp][lane*N+2] = o2;
-                if (N == 4)
-                    s_out[warp][lane*N+3] = c[3];
-                int srow = s_g.shapeYDown ? h-1-y : y;
-                P.stencil[s_g.texelOffset+size_t(srow)*w+x] = (uint8_t) flags;
-            }
-#else
-            if (i < tileEnd) {
-                int x = int(i%unsigned(w));
-                int yOut = int(i/unsigned(w));
-                int y = s_g.flip ? h-1-yOut : yOut;
-                int flags = 0;
-                // msdfErrorCorrectionInner: protection stage
-                if (P.ecMode == 2) {
-                    bool prot = false;
-                    if (needCorners)
-                        for (int j = 0; j < nRec; ++j) {
-                            int cl, cb;
-                            if (bigRecs) { cl = bigRecs[j].cornerL; cb = bigRecs[j].cornerB; }
-                            else { int2 c = s_corner[j]; cl = c.x; cb = c.y; }
-                            if (unsigned(x-cl) <= 1u && unsigned(y-cb) <= 1u)
-                                prot = true;
-                        }
-                    if (!prot)
-                        prot = protect_edges_texel<N>(e.f, x, y, sp.hRadius, sp.vRadius, sp.dRadius);
-                    if (prot)
-                        flags |= EC_FLAG_PROTECTED;
-                } else if (P.ecMode == 3)
-                    flags |= EC_FLAG_PROTECTED;
+                    prot = true;
                 // detection stage: both passes in one walk
                 TexelState k;
                 k.useBase = useBase;
-                k.protBase = (flags&EC_FLAG_PROTECTED) != 0;
+                k.protBase = prot;
                 k.useShape = useShape;
                 // protectAll() runs between the two passes when distanceCheckMode == CHECK_DISTANCE_AT_EDGE
                 k.protShape = k.protBase || (useBase && P.ecDcm == 1);
                 k.errBase = k.errShape = k.overflow = false;
                 k.texel = i;
-                find_errors_texel<N, 0, false>(e, k, x, y, sp.hSpan, sp.vSpan, sp.dSpan);
-                if (k.errBase || k.errShape)
-                    flags |= EC_FLAG_ERROR;
-                if (k.protShape && useShape)
+                k.queue = s_queue;
+                k.queueCount = &s_queueCount;
+                k.tileTexel = int(i-td.pix0);
+                find_errors_texel<N, 0, false>(e, k, x, y, sp.hSpan, sp.vSpan, sp.dSpan);     // enumerates (runs a test in place only if the queue is full)
+                s_state[i-td.pix0] = (k.protBase ? 1 : 0)|(k.protShape ? 2 : 0)|(k.errBase ? 4 : 0)|(k.errShape ? 8 : 0)|(k.overflow ? 16 : 0);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: the queued tests, dense
+        {
+            const int nQueued = s_queueCount < K2_QUEUE ? s_queueCount : K2_QUEUE;
+            for (int q = threadIdx.x; q < nQueued; q += blockDim.x) {
+                const unsigned item = s_queue[q];
+                const int owner = int(item&1023u), kind = int((item>>10)&1u), n = int((item>>11)&3u), pr = int((item>>13)&3u);
+                const unsigned io = td.pix0+unsigned(owner);
+                const int ox = int(io%unsigned(w));
+                const int oyOut = int(io/unsigned(w));
+                const int oy = s_g.flip ? h-1-oyOut : oyOut;
+                const int state = *(volatile int *) &s_state[owner];
+                TexelState t;
+                t.useBase = useBase; t.useShape = useShape;
+                t.protBase = (state&1) != 0; t.protShape = (state&2) != 0;
+                // an owner already found in error needs no exact-distance candidates (classify_point's short cut)
+                const bool knownError = (state&12) != 0;
+                t.errBase = knownError; t.errShape = false; t.overflow = false;
+                t.texel = io;
+                t.queue = nullptr; t.queueCount = nullptr; t.tileTexel = owner;
+                run_queued_test<N>(e, t, ox, oy, kind, n, pr, sp.hSpan, sp.vSpan, sp.dSpan);
+                const int bits = ((t.errBase && !knownError) ? 4 : 0)|(t.errShape ? 8 : 0)|(t.overflow ? 16 : 0);
+                if (bits)
+                    atomicOr(&s_state[owner], bits);
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: apply (:459-479), stencil, coalesced write-back
+        for (unsigned chunkBase = td.pix0+unsigned(warp)*32u; chunkBase < tileEnd; chunkBase += EC_WARPS*32u) {
+            const unsigned i = chunkBase+lane;
+            if (i < tileEnd) {
+                const int x = int(i%unsigned(w));
+                const int yOut = int(i/unsigned(w));
+                const int y = s_g.flip ? h-1-yOut : yOut;
+                const int state = s_state[i-td.pix0];
+                int flags = 0;
+                if (P.ecMode == 3 || (state&1))
                     flags |= EC_FLAG_PROTECTED;
-                if (k.overflow && !(flags&EC_FLAG_ERROR))
+                if (state&12)
+                    flags |= EC_FLAG_ERROR;
+                if ((state&2) && useShape)
+                    flags |= EC_FLAG_PROTECTED;
+                if ((state&16) && !(flags&EC_FLAG_ERROR))
                     flags |= EC_FLAG_RECHECK;
-                // apply (:459-479)
-                const float *c = e.f.at(x, y);
+                const float *c = e.f.base+size_t(i)*N;
                 float o0 = c[0], o1 = c[1], o2 = c[2];
                 if (flags&EC_FLAG_ERROR) {
                     float m = median3f(o0, o1, o2);
@@ -731,33 +675,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
                 int srow = s_g.shapeYDown ? h-1-y : y;
                 P.stencil[s_g.texelOffset+size_t(srow)*w+x] = (uint8_t) flags;
             }
-#endif
             __syncwarp();
-            // coalesced write-back of the chunk (float4 when aligned)
-            if (blocked) {
-                // four row segments of 8 texels: 8*N floats = 2*N float4 each, 16-byte aligned
-                const int perSeg = 2*N;
-                if (lane < 4*perSeg) {
-                    int seg = lane/perSeg, j = lane%perSeg;
-                    float *dst = P.out+s_g.outOffset+(size_t(blockOrigin)+size_t(seg)*w)*N;
-                    reinterpret_cast<float4 *>(dst)[j] = reinterpret_cast<const float4 *>(s_out[warp]+seg*8*N)[j];
-                }
+            // 32 consecutive texels of the glyph block: float4 when aligned
+            unsigned nPix = tileEnd-chunkBase < 32u ? tileEnd-chunkBase : 32u;
+            int nFloats = int(nPix)*N;
+            float *dst = P.out+s_g.outOffset+size_t(chunkBase)*N;
+            if ((reinterpret_cast<uintptr_t>(dst)&15) == 0) {
+                int n4 = nFloats>>2;
+                const float4 *s4 = reinterpret_cast<const float4 *>(s_out[warp]);
+                float4 *d4 = reinterpret_cast<float4 *>(dst);
+                for (int q = lane; q < n4; q += 32)
+                    d4[q] = s4[q];
+                for (int q = (n4<<2)+lane; q < nFloats; q += 32)
+                    dst[q] = s_out[warp][q];
             } else {
-                unsigned nPix = tileEnd-chunkBase < 32u ? tileEnd-chunkBase : 32u;
-                int nFloats = int(nPix)*N;
-                float *dst = P.out+s_g.outOffset+size_t(chunkBase)*N;
-                if ((reinterpret_cast<uintptr_t>(dst)&15) == 0) {
-                    int n4 = nFloats>>2;
-                    const float4 *s4 = reinterpret_cast<const float4 *>(s_out[warp]);
-                    float4 *d4 = reinterpret_cast<float4 *>(dst);
-                    for (int q = lane; q < n4; q += 32)
-                        d4[q] = s4[q];
-                    for (int q = (n4<<2)+lane; q < nFloats; q += 32)
-                        dst[q] = s_out[warp][q];
-                } else {
-                    for (int q = lane; q < nFloats; q += 32)
-                        dst[q] = s_out[warp][q];
-                }
+                for (int q = lane; q < nFloats; q += 32)
+                    dst[q] = s_out[warp][q];
             }
             __syncwarp();
         }
