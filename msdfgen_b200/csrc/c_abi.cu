@@ -119,13 +119,14 @@ struct b200msdf_batch {
     DevBuf filt, tileFilt;        // k1a -> k1b filter words (sized at launch) and the small tiles' word offsets: [overlap][tile], [simple][tile]
     size_t filtWords[2] = { 0, 0 };
     std::vector<unsigned long long> hTileFilt;
+    DevBuf scratchW;
     DevBuf counters, scratch;     // per batch, so that batches launched on different streams never share scheduling state
     std::vector<GlyphDesc> hGlyphs;
     std::vector<TileDesc> hTiles;
     std::vector<int> hBig;
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
-        bigGlyphs.release(); bigRecs.release(); bigCull.release(); bigPerp.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); bytes.release(); byteTargets.release(); signMatch.release();
+        bigGlyphs.release(); bigRecs.release(); bigCull.release(); bigPerp.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); scratchW.release(); bytes.release(); byteTargets.release(); signMatch.release();
         blocks.release(); blockWork.release(); filt.release(); tileFilt.release(); k1Counters.release();
     }
 };
@@ -509,12 +510,18 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
         if ((rc = b->blockWork.reserve(capBytes+(size_t) grid*P.listPerCta*sizeof(int)))) return rc;
         P.blockCaps = b->blockWork.as<unsigned long long>();
         P.blockList = reinterpret_cast<int *>(static_cast<char *>(b->blockWork.p)+capBytes);
+        // parked per contour and texel (shape_distance_fold): NOUT resolved distances + one byte of winding
         P.scratchStride = (size_t) grid*CTA_THREADS;
-        if (scratch > 0) {
-            if ((rc = b->scratch.reserve(P.scratchStride*(size_t) scratch*sizeof(double)))) return rc;
+        if (OVERLAP && b->maxBigContours > B200_LOCAL_CONTOURS) {
+            const size_t slots = P.scratchStride*(size_t) b->maxBigContours;
+            if ((rc = b->scratch.reserve(slots*ModeTraits<MODE>::NOUT*sizeof(double)))) return rc;
+            if ((rc = b->scratchW.reserve(slots))) return rc;
             P.scratch = b->scratch.as<double>();
-        } else
+            P.scratchW = b->scratchW.as<signed char>();
+        } else {
             P.scratch = nullptr;
+            P.scratchW = nullptr;
+        }
         P.counterIndex = 3;
         k1_big_blocks<MODE, OVERLAP><<<grid, CTA_THREADS, subListBytes, ctx->stream>>>(P);
         CUDA_TRY(cudaGetLastError());

@@ -1038,6 +1038,199 @@ __device__ __forceinline__ void shape_distance_over(const SegRec *recs, int nRec
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The overlapping combiner with the shape / inner / outer selectors FOLDED while the contours are walked (big shapes).
+//
+// OverlappingContourCombiner::distance (contour-combiners.cpp:78-134) merges every contour's selector into three selectors and
+// afterwards only needs, per contour, its resolved distance(s) and winding.  Parking whole selector states per contour and texel
+// (the small-glyph kernels do, for <= 4 contours in local memory) costs 32-150 bytes per contour and texel; a 100-contour shape
+// at 4096x4096 then moves > 100 GB through L2/HBM.  Here a finished contour is merged at once into three accumulators held in
+// registers and only its resolved distances (+ one byte of winding) are parked: 9 bytes per contour and texel for an SDF.
+// A merged channel's computeDistance needs the nearest edge only through dd = the edge's distance after
+// distanceToPerpendicularDistance, which depends on (d, edge, p) alone — so it is evaluated once per contour and travels with
+// the minimum through the merges (same argument as combine_parked in distance_filter.cuh).
+struct FoldStore {
+    double *base;           // resolved distances: NOUT per contour
+    signed char *wbase;     // windings
+    size_t stride;          // element stride between consecutive contours' slots of one thread (1 = private arrays)
+    int perContour;
+    __device__ __forceinline__ double &cd(int c, int k) { return base[(size_t(c)*perContour+k)*stride]; }
+    __device__ __forceinline__ signed char &w(int c) { return wbase[size_t(c)*stride]; }
+};
+
+template <int MODE> struct FoldAcc {
+    double d[ModeTraits<MODE>::NCH], dot[ModeTraits<MODE>::NCH], dd[ModeTraits<MODE>::NCH], neg[ModeTraits<MODE>::NCH], pos[ModeTraits<MODE>::NCH];
+};
+
+template <int MODE>
+__device__ __forceinline__ void fold_init(FoldAcc<MODE> &a) {
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NCH; ++k) { a.d[k] = -DBL_MAX; a.dot[k] = 0; a.dd[k] = DBL_MAX; a.neg[k] = -DBL_MAX; a.pos[k] = DBL_MAX; }
+}
+
+template <int MODE>
+__device__ __forceinline__ void fold_merge(FoldAcc<MODE> &a, const Sel<MODE> &s, const double *dd) {
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NCH; ++k) {
+        if (sd_less(s.ch[k].d, s.ch[k].dot, a.d[k], a.dot[k])) { a.d[k] = s.ch[k].d; a.dot[k] = s.ch[k].dot; a.dd[k] = dd[k]; }
+        if (MODE != 1) {
+            if (s.ch[k].neg > a.neg[k]) a.neg[k] = s.ch[k].neg;
+            if (s.ch[k].pos < a.pos[k]) a.pos[k] = s.ch[k].pos;
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void fold_distance(const FoldAcc<MODE> &a, double *out) {
+    const int NCH = ModeTraits<MODE>::NCH;
+    double td = a.d[0], tdot = a.dot[0];
+    #pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        double v = a.d[k];
+        if (MODE != 1) {
+            const double m = a.d[k] < 0 ? a.neg[k] : a.pos[k];
+            v = fabs(a.dd[k]) < fabs(m) ? a.dd[k] : m;
+        }
+        out[k] = v;
+        if (MODE == 4 && k > 0 && sd_less(a.d[k], a.dot[k], td, tdot)) { td = a.d[k]; tdot = a.dot[k]; }
+    }
+    if (MODE == 4)
+        out[3] = td;
+}
+
+// the nearest edge's distance after distanceToPerpendicularDistance (edge-segments.cpp:28-52); DBL_MAX = no nearest edge
+__device__ __noinline__ double near_edge_dd(double cd, int near, const SegRec *recs, double px, double py) {
+    if (near < 0)
+        return DBL_MAX;
+    double dd = cd;
+    const int side = near&3;
+    if (side) {
+        const d2 p = mk(px, py);
+        const SegRec &s = recs[near>>2];
+        if (side == 1) {
+            d2 aq = p-s.p0;
+            if (dot(aq, s.aDirNZ) < 0) {
+                double pd = cross(aq, s.aDirNZ);
+                if (fabs(pd) <= fabs(dd))
+                    dd = pd;
+            }
+        } else {
+            d2 bq = p-s.pEnd;
+            if (dot(bq, s.bDirNZ) > 0) {
+                double pd = cross(bq, s.bDirNZ);
+                if (fabs(pd) <= fabs(dd))
+                    dd = pd;
+            }
+        }
+    }
+    return dd;
+}
+
+template <int MODE, typename IT>
+__device__ __forceinline__ void shape_distance_fold(const SegRec *recs, int nRec, IT it, d2 p, FoldStore st, double *out) {
+    const int NCH = ModeTraits<MODE>::NCH;
+    const int NOUT = ModeTraits<MODE>::NOUT;
+    FoldAcc<MODE> shape, inner, outer;
+    fold_init(shape); fold_init(inner); fold_init(outer);
+    int nc = 0;
+    {
+        Sel<MODE> cur;
+        sel_init(cur);
+        int j0 = 0;
+        while (j0 < nRec) {
+            const int j1 = it.group_last(recs, j0, nRec);
+            double cap[NCH];
+            distance_caps<MODE>(recs, it, j0, j1, p, cap);
+            for (int i = j0; i <= j1; ++i) {
+                const int j = it.at(i);
+                sel_add_edge<MODE>(cur, recs[j], j, p, cap);
+            }
+            // the contour's own distances (computeDistance per channel) ...
+            double dd[NCH], cd[NOUT];
+            double td = cur.ch[0].d, tdot = cur.ch[0].dot;
+            #pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                cd[k] = cur.ch[k].d;
+                dd[k] = DBL_MAX;
+                if (MODE != 1) {
+                    dd[k] = near_edge_dd(cur.ch[k].d, cur.ch[k].near, recs, p.x, p.y);
+                    const double m = cur.ch[k].d < 0 ? cur.ch[k].neg : cur.ch[k].pos;
+                    cd[k] = fabs(dd[k]) < fabs(m) ? dd[k] : m;
+                }
+                if (MODE == 4 && k > 0 && sd_less(cur.ch[k].d, cur.ch[k].dot, td, tdot)) { td = cur.ch[k].d; tdot = cur.ch[k].dot; }
+            }
+            if (MODE == 4)
+                cd[3] = td;
+            // ... its merges (contour-combiners.cpp:84-92) ...
+            const int w = recs[it.at(j1)].winding;
+            const double rd = resolve<MODE>(cd);
+            fold_merge<MODE>(shape, cur, dd);
+            if (w > 0 && rd >= 0)
+                fold_merge<MODE>(inner, cur, dd);
+            if (w < 0 && rd <= 0)
+                fold_merge<MODE>(outer, cur, dd);
+            // ... and what the second half of the combiner reads back
+            #pragma unroll
+            for (int k = 0; k < NOUT; ++k)
+                st.cd(nc, k) = cd[k];
+            st.w(nc) = (signed char) w;
+            sel_init(cur);
+            ++nc;
+            j0 = j1+1;
+        }
+    }
+    double shapeD[NOUT], innerD[NOUT], outerD[NOUT], dist[NOUT];
+    fold_distance<MODE>(shape, shapeD);
+    fold_distance<MODE>(inner, innerD);
+    fold_distance<MODE>(outer, outerD);
+    const double innerScalar = resolve<MODE>(innerD), outerScalar = resolve<MODE>(outerD);
+    int winding;
+    if (innerScalar >= 0 && fabs(innerScalar) <= fabs(outerScalar)) {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) dist[k] = innerD[k];
+        winding = 1;
+    } else if (outerScalar <= 0 && fabs(outerScalar) < fabs(innerScalar)) {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) dist[k] = outerD[k];
+        winding = -1;
+    } else {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) out[k] = shapeD[k];
+        return;
+    }
+    // Pass 0: same-winding contours refine the inner/outer pick.  Pass 1: the others may override it.
+    for (int pass = 0; pass < 2; ++pass)
+        for (int c = 0; c < nc; ++c) {
+            const int w = st.w(c);
+            // (the winding test first: it spares the loads of the distances of half the contours)
+            if (pass == 0 ? w != winding : w == winding)
+                continue;
+            double cd[NOUT];
+            #pragma unroll
+            for (int k = 0; k < NOUT; ++k)
+                cd[k] = st.cd(c, k);
+            const double rc = resolve<MODE>(cd), rdist = resolve<MODE>(dist);
+            bool take;
+            if (pass == 0) {
+                if (winding > 0)
+                    take = fabs(rc) < fabs(outerScalar) && rc > rdist;
+                else
+                    take = fabs(rc) < fabs(innerScalar) && rc < rdist;
+            } else
+                take = rc*rdist >= 0 && fabs(rc) < fabs(rdist);
+            if (take) {
+                #pragma unroll
+                for (int k = 0; k < NOUT; ++k) dist[k] = cd[k];
+            }
+        }
+    if (resolve<MODE>(dist) == resolve<MODE>(shapeD)) {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) dist[k] = shapeD[k];
+    }
+    #pragma unroll
+    for (int k = 0; k < NOUT; ++k) out[k] = dist[k];
+}
+
 template <int MODE, bool OVERLAP>
 __device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, d2 p, ContourStore store, double *out) {
     shape_distance_over<MODE, OVERLAP>(recs, nRec, SeqIter(), p, store, out);

@@ -56,6 +56,7 @@ struct KernelParams {
     unsigned long long *blockCaps;// per-CTA workspace: capStride squared distances (as ordered bit patterns)
     size_t listStride, listPerCta, capStride;   // list capacity; ints per CTA (list + group ends); cap slots per CTA
     double *scratch;              // per-thread contour-distance slices for many-contour shapes
+    signed char *scratchW;        // k1_big_blocks: per-thread winding slices (same indexing)
     size_t scratchStride;         // = gridDim.x * CTA_THREADS
     unsigned *filt;               // k1a -> k1b: per-unit filter words (distance_filter.cuh)
     const unsigned long long *tileFilt;   // word offset of every small tile's first unit in filt
@@ -567,7 +568,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
     __shared__ int s_subEnd[OVERLAP ? WARPS : 1][OVERLAP ? SUB_GROUPS : 1];
     int *list = P.blockList+size_t(blockIdx.x)*P.listPerCta;
     unsigned long long *caps = P.blockCaps+size_t(blockIdx.x)*P.capStride;
-    double localStore[OVERLAP ? B200_LOCAL_CONTOURS*StoreLayout<MODE>::PER_CONTOUR : 1];
+    double localCd[OVERLAP ? B200_LOCAL_CONTOURS*NOUT : 1];
+    signed char localW[OVERLAP ? B200_LOCAL_CONTOURS : 1];
     const unsigned lane = threadIdx.x&31, warp = threadIdx.x>>5;
     int stagedGlyph = -1;
     for (;;) {
@@ -677,13 +679,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
                 __syncthreads();
             }
         }
-        ContourStore store;
-        store.perContour = StoreLayout<MODE>::PER_CONTOUR;
+        // parked per contour and texel: the resolved distance(s) and the winding (shape_distance_fold)
+        FoldStore store;
+        store.perContour = NOUT;
         if (OVERLAP && s_g.nonEmptyContours > B200_LOCAL_CONTOURS) {
             store.base = P.scratch+(size_t(blockIdx.x)*CTA_THREADS+threadIdx.x);
+            store.wbase = P.scratchW+(size_t(blockIdx.x)*CTA_THREADS+threadIdx.x);
             store.stride = P.scratchStride;
         } else {
-            store.base = localStore;
+            store.base = localCd;
+            store.wbase = localW;
             store.stride = 1;
         }
         // ---- the texels; a warp takes an 8x4 sub-block per pass, like k1_distance_field
@@ -769,7 +774,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
                 const int y = s_g.flip ? h-1-yOut : yOut;
                 d2 p = mk((s_g.x0+x+.5)/s_g.sx-s_g.tx, (s_g.y0+y+.5)/s_g.sy-s_g.ty);
                 double dist[NOUT];
-                shape_distance_over<MODE, OVERLAP>(recs, nWalk, it, p, store, dist);
+                if (OVERLAP)
+                    shape_distance_fold<MODE>(recs, nWalk, it, p, store, dist);
+                else
+                    shape_distance_over<MODE, false>(recs, nWalk, it, p, ContourStore(), dist);
                 #pragma unroll
                 for (int k = 0; k < NOUT; ++k)
                     s_out[(yl*BLOCK_W+xl)*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));
