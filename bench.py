@@ -288,6 +288,14 @@ class Rig:
         if world > 1:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         self.ctx = api.Context(local_rank)
+        # one process per GPU: keep this rank's host thread and the pinned buffers it allocates on the GPU's NUMA node
+        self.numa_cpus = None
+        self.affinity0 = os.sched_getaffinity(0)
+        if os.environ.get("B200MSDF_NO_NUMA_BIND") is None:
+            try:
+                self.numa_cpus = self.ctx.bind_host_thread()
+            except Exception:
+                self.numa_cpus = None
         self.stream = torch.cuda.current_stream()
         self.flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -547,6 +555,8 @@ def main():
                        "parallelism": (f"glyph sharding x{world}, no data-path collective" if cfg["kind"] == "atlas" else
                                        f"row bands x{world}; {res.get('collective')}")},
             "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "clocks": clocks, "wall_s": w1 - w0}
+    line["config"]["host_binding"] = (f"rank thread + pinned buffers on the GPU's NUMA node ({rig.numa_cpus} CPUs, b200msdf_bind_host_thread)"
+                                      if rig.numa_cpus else "none")
     for k in ("glyphs_this_rank", "segments_this_rank", "rows_this_rank", "segments", "contours", "broadcast_ms", "seams_bit_identical"):
         if k in res:
             line["config"][k] = res[k]
@@ -568,6 +578,7 @@ def main():
         line["configs"] = ex
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
+        os.sched_setaffinity(0, rig.affinity0)          # the CPU leg uses every core of the box, not just the GPU's NUMA node
         threads = host_threads()
         if cfg["kind"] == "atlas":
             cb = cpu_atlas_rates(parts["main"][0], parts["main"][1], cfg["size"], cfg["mode"], args.cpu_sample, threads)

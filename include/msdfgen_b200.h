@@ -119,6 +119,14 @@ int b200msdf_set_stream(b200msdf_ctx *ctx, void *cuda_stream, int use_own);
 int b200msdf_synchronize(b200msdf_ctx *ctx);
 /* Number of kernels this context has launched so far (for bench.py's gpu_launches). */
 uint64_t b200msdf_launch_count(const b200msdf_ctx *ctx);
+/* Pins the calling host thread to the CPUs local to the context's GPU (its NUMA node); pinned buffers allocated by the thread
+ * afterwards are local to the GPU too.  Returns the number of CPUs in the new affinity mask (> 0) or a negative error code.
+ * Optional: one process per GPU on a multi-socket host should call it once before allocating its host buffers. */
+int b200msdf_bind_host_thread(b200msdf_ctx *ctx);
+/* Diagnostics: how many times the literal closed-form cubic solver (equation-solver.cpp:34-61 with correctly rounded acos / cos /
+ * pow) has run on this device since the last reset — cusp segments, and the guard-band fallbacks of the fast foot-point root
+ * path (a polished root within 1e-9 of 0 or 1, or a distance within 1e-13 of a tie).  Synchronises the context's stream. */
+int b200msdf_debug_exact_root_calls(b200msdf_ctx *ctx, int reset, uint64_t *calls);
 /* Pinned host memory for callers that want DMA-speed transfers. */
 int b200msdf_host_alloc(void **ptr, size_t bytes);
 void b200msdf_host_free(void *ptr);
@@ -173,6 +181,15 @@ int b200msdf_rasterize(b200msdf_ctx *ctx, const b200msdf_shapes *shapes, const b
  * ignored, as in the reference. */
 int b200msdf_render_sdf(b200msdf_ctx *ctx, const b200msdf_bitmap *output, int out_channels, const b200msdf_bitmap *sdf, int sdf_channels,
                         double px_range_lower, double px_range_upper, float sd_threshold);
+
+/* estimateSDFError (core/sdf-error-estimation.h:19-21, sdf-error-estimation.cpp:134-154) for every bitmap of a batch: the fraction
+ * of the scanned length on which the distance field (1, 3 or 4 channels) and the shape disagree about inside / outside,
+ * scanlines_per_row sub-rows per bitmap row.  errors[n_glyphs] receives the values (0 for bitmaps narrower or lower than 2 texels,
+ * NaN if one scanline crosses more than 2048 edges or the projection's x scale is not positive — the reference does not terminate
+ * for a mirrored projection).  Like the reference, the field's rows are taken as they lie in memory and
+ * flipped only by the SHAPE's y_downward flag; bitmap.y_downward is ignored. */
+int b200msdf_estimate_sdf_error(b200msdf_ctx *ctx, int channels, const b200msdf_shapes *shapes, const b200msdf_transform *transformations,
+                                int transform_per_glyph, const b200msdf_bitmap *sdfs, int scanlines_per_row, int fill_rule, double *errors);
 
 /* simulate8bit (core/render-sdf.h:19-21): snaps every float of the bitmap to the value an 8-bit image would hold. */
 int b200msdf_simulate_8bit(b200msdf_ctx *ctx, const b200msdf_bitmap *bitmap, int channels);

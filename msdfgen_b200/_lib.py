@@ -15,9 +15,9 @@ LIB_PATH = os.environ.get("B200MSDF_LIB") or os.path.join(HERE, "libmsdfgen_b200
 # Every symbol include/msdfgen_b200.h declares (checked by tests/test_abi.py without a GPU).
 EXPORTS = [
     "b200msdf_version", "b200msdf_last_error", "b200msdf_default_config", "b200msdf_create", "b200msdf_destroy",
-    "b200msdf_set_stream", "b200msdf_synchronize", "b200msdf_launch_count", "b200msdf_host_alloc", "b200msdf_host_free",
+    "b200msdf_set_stream", "b200msdf_synchronize", "b200msdf_launch_count", "b200msdf_bind_host_thread", "b200msdf_debug_exact_root_calls", "b200msdf_host_alloc", "b200msdf_host_free",
     "b200msdf_generate", "b200msdf_generate_batch", "b200msdf_generate_batch_u8", "b200msdf_error_correction", "b200msdf_fast_error_correction",
-    "b200msdf_sign_correction", "b200msdf_rasterize", "b200msdf_batch_sign_correction", "b200msdf_render_sdf", "b200msdf_simulate_8bit",
+    "b200msdf_sign_correction", "b200msdf_rasterize", "b200msdf_batch_sign_correction", "b200msdf_render_sdf", "b200msdf_simulate_8bit", "b200msdf_estimate_sdf_error",
     "b200msdf_batch_upload", "b200msdf_batch_upload_regions", "b200msdf_batch_launch", "b200msdf_batch_launch_stages", "b200msdf_batch_device_output", "b200msdf_batch_device_stencil",
     "b200msdf_batch_output_floats", "b200msdf_batch_glyph_offset", "b200msdf_batch_download", "b200msdf_batch_free",
 ]
@@ -75,6 +75,10 @@ def load():
     lib.b200msdf_synchronize.argtypes = [vp]
     lib.b200msdf_launch_count.argtypes = [vp]
     lib.b200msdf_launch_count.restype = u64
+    lib.b200msdf_debug_exact_root_calls.argtypes = [vp, i32, C.POINTER(u64)]
+    lib.b200msdf_debug_exact_root_calls.restype = i32
+    lib.b200msdf_bind_host_thread.argtypes = [vp]
+    lib.b200msdf_bind_host_thread.restype = i32
     lib.b200msdf_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.b200msdf_host_free.argtypes = [vp]
     lib.b200msdf_host_free.restype = None

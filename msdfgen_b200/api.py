@@ -173,6 +173,19 @@ class Context:
         buf = (C.c_uint8 * max(count * dtype.itemsize, 1)).from_address(ptr.value)
         return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
 
+    def exact_root_calls(self, reset=False):
+        """Runs of the literal (correctly rounded) cubic solver on this device since the last reset."""
+        v = C.c_uint64(0)
+        _lib.check(self.lib.b200msdf_debug_exact_root_calls(self.h, int(reset), C.byref(v)))
+        return int(v.value)
+
+    def bind_host_thread(self):
+        """Pin the calling thread to the CPUs of the GPU's NUMA node (call before allocating pinned buffers); returns the CPU count."""
+        n = self.lib.b200msdf_bind_host_thread(self.h)
+        if n <= 0:
+            raise RuntimeError(self.lib.b200msdf_last_error().decode())
+        return n
+
     def release_pinned(self):
         """Frees every block handed out by pinned() (the arrays must no longer be used)."""
         self.synchronize()
@@ -251,6 +264,16 @@ class Context:
         s = _shapes_struct(shapes)
         _lib.check(self.lib.b200msdf_rasterize(self.h, C.byref(s), xf, per, bms, fill_rule))
         return outputs
+
+    def estimate_sdf_error(self, sdfs, shapes: FlatShapes, transformations, scanlines_per_row=4, fill_rule=FILL_NONZERO):
+        """estimateSDFError (core/sdf-error-estimation.h:19) for every [h,w,N] field of the list -> float64[n_glyphs]."""
+        xf, per = _transforms(transformations)
+        bms = _bitmaps(sdfs, shapes.n_glyphs)
+        s = _shapes_struct(shapes)
+        out = np.zeros(shapes.n_glyphs, np.float64)
+        _lib.check(self.lib.b200msdf_estimate_sdf_error(self.h, sdfs[0].shape[2], C.byref(s), xf, per, bms, int(scanlines_per_row), int(fill_rule),
+                                                        out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     def render_sdf(self, output, sdf, sdf_px_range=(0.0, 0.0), sd_threshold=0.5):
         """renderSDF (core/render-sdf.h:11-16): output float32 [oh,ow,NO] <- sdf float32 [h,w,NI]; sdf_px_range a number or (lower, upper)."""
@@ -384,6 +407,11 @@ def rasterize(output, shape, projection, fillRule=FILL_NONZERO, **kw):
 def renderSDF(output, sdf, sdfPxRange=0.0, sdThreshold=0.5):
     """core/render-sdf.h:11-16"""
     return default_context().render_sdf(output, sdf, sdfPxRange, sdThreshold)
+
+
+def estimateSDFError(sdf, shape, transformation, scanlinesPerRow, fillRule=FILL_NONZERO):
+    """core/sdf-error-estimation.h:19-21"""
+    return float(default_context().estimate_sdf_error([sdf], shape, transformation, scanlinesPerRow, fillRule)[0])
 
 
 def simulate8bit(bitmap):

@@ -5,7 +5,12 @@
 #include "error_correction.cuh"
 #include "scanline.cuh"
 #include "render.cuh"
+#include "sdf_error.cuh"
 
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <sched.h>
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
@@ -853,6 +858,67 @@ int b200msdf_synchronize(b200msdf_ctx *ctx) {
 
 uint64_t b200msdf_launch_count(const b200msdf_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int b200msdf_debug_exact_root_calls(b200msdf_ctx *ctx, int reset, uint64_t *calls) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    unsigned long long v = 0;
+    CUDA_TRY(cudaMemcpyFromSymbol(&v, g_exactRootCalls, sizeof(v)));
+    if (calls) *calls = v;
+    if (reset) {
+        v = 0;
+        CUDA_TRY(cudaMemcpyToSymbol(g_exactRootCalls, &v, sizeof(v)));
+    }
+    return 0;
+}
+
+int b200msdf_bind_host_thread(b200msdf_ctx *ctx) {
+    // Pins the calling thread to the CPUs next to the context's GPU (sysfs local_cpulist of its PCI function).  Pinned host
+    // buffers the thread allocates afterwards land on that NUMA node, and the zero-copy stores / DMA of the host-buffer entry
+    // points no longer cross the inter-socket link — with one process per GPU on a two-socket box this is what keeps the
+    // end-to-end rate from dropping when all GPUs run at once.
+    int rc = bind(ctx);
+    if (rc) return rc;
+    char busId[32] = { 0 };
+    CUDA_TRY(cudaDeviceGetPCIBusId(busId, (int) sizeof(busId), ctx->device));
+    for (char *c = busId; *c; ++c)
+        if (*c >= 'A' && *c <= 'Z') *c = (char) (*c-'A'+'a');
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", busId);
+    FILE *f = fopen(path, "r");
+    if (!f)
+        return fail(B200MSDF_ERR_ARG, "cannot read %s", path);
+    char list[1024] = { 0 };
+    const bool got = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!got)
+        return fail(B200MSDF_ERR_ARG, "%s is empty", path);
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n = 0;
+    for (const char *c = list; *c && *c != '\n';) {
+        char *end;
+        long a = strtol(c, &end, 10), b2 = a;
+        if (end == c) break;
+        if (*end == '-') { c = end+1; b2 = strtol(c, &end, 10); }
+        for (long k = a; k <= b2 && k < CPU_SETSIZE; ++k) { CPU_SET((int) k, &set); ++n; }
+        c = *end == ',' ? end+1 : end;
+    }
+    if (n == 0)
+        return fail(B200MSDF_ERR_ARG, "no CPUs listed in %s", path);
+    // keep to what the process is allowed to use (cgroup / taskset)
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+        cpu_set_t both;
+        CPU_AND(&both, &set, &allowed);
+        if (CPU_COUNT(&both) > 0)
+            set = both;
+    }
+    if (sched_setaffinity(0, sizeof(set), &set) != 0)
+        return fail(B200MSDF_ERR_ARG, "sched_setaffinity failed");
+    return CPU_COUNT(&set);
+}
+
 int b200msdf_host_alloc(void **ptr, size_t bytes) {
     if (!ptr)
         return fail(B200MSDF_ERR_ARG, "null pointer");
@@ -1293,6 +1359,99 @@ int b200msdf_simulate_8bit(b200msdf_ctx *ctx, const b200msdf_bitmap *bitmap, int
     CUDA_TRY(cudaGetLastError());
     ++ctx->launches;
     return download_image(ctx, b->out, bitmap, channels);
+}
+
+int b200msdf_estimate_sdf_error(b200msdf_ctx *ctx, int channels, const b200msdf_shapes *shapes, const b200msdf_transform *xf, int xfPerGlyph,
+                                const b200msdf_bitmap *sdfs, int scanlines_per_row, int fill_rule, double *errors) {
+    int rc = bind(ctx);
+    if (rc) return rc;
+    if (channels != 1 && channels != 3 && channels != 4)
+        return fail(B200MSDF_ERR_ARG, "estimateSDFError needs 1, 3 or 4 channels");
+    if (fill_rule < 0 || fill_rule > 3)
+        return fail(B200MSDF_ERR_ARG, "fill rule out of range");
+    if (!errors)
+        return fail(B200MSDF_ERR_ARG, "null result array");
+    if ((rc = check_shapes(shapes))) return rc;
+    if ((rc = check_bitmaps(sdfs, shapes->n_glyphs))) return rc;
+    const int n = shapes->n_glyphs;
+    if (n == 0)
+        return 0;
+    std::vector<int32_t> dims;
+    std::vector<uint8_t> yd;
+    dims_from_bitmaps(sdfs, n, dims, yd);
+    b200msdf_batch *b = &ctx->pool;
+    const int mode = channels == 1 ? B200MSDF_SDF : channels == 3 ? B200MSDF_MSDF : B200MSDF_MTSDF;
+    if ((rc = upload_batch(ctx, b, mode, shapes, xf, xfPerGlyph, dims.data(), 1, nullptr))) return rc;
+    // scanlines: (height-1) x scanlinesPerRow per bitmap; sdf-error-estimation.cpp:135-136 returns 0 for degenerate inputs
+    std::vector<unsigned> scanBase((size_t) n+1, 0u);
+    int maxW = 0;
+    for (int g = 0; g < n; ++g) {
+        const GlyphDesc &d = b->hGlyphs[(size_t) g];
+        const bool empty = d.w <= 1 || d.h <= 1 || scanlines_per_row < 1;
+        scanBase[(size_t) g+1] = scanBase[(size_t) g]+(empty ? 0u : (unsigned) (d.h-1)*(unsigned) scanlines_per_row);
+        if (d.w > maxW) maxW = d.w;
+    }
+    const unsigned total = scanBase[(size_t) n];
+    for (int g = 0; g < n; ++g)
+        errors[g] = 0;
+    if (total == 0)
+        return 0;
+    // the caller's fields in the batch's packed layout (rows as they lie in the caller's memory)
+    if ((rc = ctx->pinIn.reserve(b->outFloats*4))) return rc;
+    float *h = static_cast<float *>(ctx->pinIn.p);
+    for (int g = 0; g < n; ++g) {
+        const GlyphDesc &d = b->hGlyphs[(size_t) g];
+        for (int r = 0; r < d.h; ++r)
+            memcpy(h+d.outOffset+(size_t) r*d.w*channels, sdfs[g].pixels+(ptrdiff_t) sdfs[g].row_stride*r, sizeof(float)*(size_t) d.w*channels);
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->out.p, h, b->outFloats*4, cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = (int) (total < (unsigned) ctx->numSMs*16u ? total : (unsigned) ctx->numSMs*16u);
+    SdfErrorParams E;
+    memset(&E, 0, sizeof(E));
+    KernelParams P;
+    b200msdf_config cfg;
+    b200msdf_default_config(&cfg);
+    fill_params(ctx, b, &cfg, P);
+    E.raw = P.raw;
+    E.glyphs = P.glyphs;
+    E.sdf = b->out.as<float>();
+    E.nGlyphs = n;
+    E.scanlinesPerRow = scanlines_per_row;
+    E.fillRule = fill_rule;
+    E.slabStride = (size_t) 3*maxW+8;
+    E.totalScanlines = total;
+    // scratch: scan bases, per-scanline results, per-CTA slabs
+    const size_t baseBytes = ((size_t) n+1)*sizeof(unsigned), outBytes = (size_t) total*sizeof(double);
+    const size_t slabX = (size_t) grid*E.slabStride*sizeof(double), slabD = (size_t) grid*E.slabStride*sizeof(int);
+    const size_t offOut = (baseBytes+15)&~size_t(15), offX = offOut+((outBytes+15)&~size_t(15)), offD = offX+((slabX+15)&~size_t(15));
+    if ((rc = b->scratch.reserve(offD+slabD+64))) return rc;
+    char *sc = static_cast<char *>(b->scratch.p);
+    CUDA_TRY(cudaMemcpyAsync(sc, scanBase.data(), baseBytes, cudaMemcpyHostToDevice, ctx->stream));
+    E.scanBase = reinterpret_cast<const unsigned *>(sc);
+    E.out = reinterpret_cast<double *>(sc+offOut);
+    E.slabX = reinterpret_cast<double *>(sc+offX);
+    E.slabDir = reinterpret_cast<int *>(sc+offD);
+    switch (channels) {
+        case 1: k7_sdf_error<1><<<grid, SE_THREADS, 0, ctx->stream>>>(E); break;
+        case 3: k7_sdf_error<3><<<grid, SE_THREADS, 0, ctx->stream>>>(E); break;
+        default: k7_sdf_error<4><<<grid, SE_THREADS, 0, ctx->stream>>>(E); break;
+    }
+    CUDA_TRY(cudaGetLastError());
+    ++ctx->launches;
+    std::vector<double> per((size_t) total);
+    CUDA_TRY(cudaMemcpyAsync(per.data(), E.out, outBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    // error += ... in the reference's order (rows, then sub-rows), then the mean
+    for (int g = 0; g < n; ++g) {
+        const unsigned s0 = scanBase[(size_t) g], s1 = scanBase[(size_t) g+1];
+        if (s1 == s0)
+            continue;
+        double error = 0;
+        for (unsigned k = s0; k < s1; ++k)
+            error += per[k];
+        errors[g] = error/(double) ((b->hGlyphs[(size_t) g].h-1)*scanlines_per_row);
+    }
+    return 0;
 }
 
 int b200msdf_batch_sign_correction(b200msdf_ctx *ctx, b200msdf_batch *batch, float sdf_zero_value, int fill_rule) {

@@ -20,6 +20,7 @@
 #include <cfloat>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "cr_math.cuh"
 
 namespace b200 {
 
@@ -355,9 +356,13 @@ __device__ __forceinline__ Roots solve_quadratic(double a, double b, double c) {
     return r;
 }
 
-// (cold: only reached from the fast path when its fp32 stage cannot represent the coefficients — kept out of line)
+// solveCubicNormed (equation-solver.cpp:34-61) with correctly rounded acos / cos / pow (cr_math.cuh): reproduces the reference's
+// roots to the bit wherever the host libm rounds correctly.  Cold: cusp segments (SEG_EXACT_ROOTS) and the fast path's guard-band
+// and range fallbacks — kept out of line.
+__device__ unsigned long long g_exactRootCalls;     // how often the literal solver ran (b200msdf_debug_exact_root_calls)
 __device__ __noinline__ Roots solve_cubic_normed(double a, double b, double c) {
     Roots x; x.t0 = x.t1 = x.t2 = 0;
+    atomicAdd(&g_exactRootCalls, 1ull);
     double a2 = a*a;
     double q = 1/9.*(a2-3*b);
     double r = 1/54.*(a*(2*a2-9*b)+27*c);
@@ -368,14 +373,14 @@ __device__ __noinline__ Roots solve_cubic_normed(double a, double b, double c) {
         double t = r/sqrt(q3);
         if (t < -1) t = -1;
         if (t > 1) t = 1;
-        t = acos(t);
+        t = crm::cr_acos(t);
         q = -2*sqrt(q);
-        x.t0 = q*cos(1/3.*t)-a;
-        x.t1 = q*cos(1/3.*(t+2*3.14159265358979323846))-a;
-        x.t2 = q*cos(1/3.*(t-2*3.14159265358979323846))-a;
+        x.t0 = q*crm::cr_cos(1/3.*t)-a;
+        x.t1 = q*crm::cr_cos(1/3.*(t+2*3.14159265358979323846))-a;
+        x.t2 = q*crm::cr_cos(1/3.*(t-2*3.14159265358979323846))-a;
         x.n = 3;
     } else {
-        double u = (r < 0 ? 1 : -1)*pow(fabs(r)+sqrt(r2-q3), 1/3.);
+        double u = (r < 0 ? 1 : -1)*crm::cr_pow_third(fabs(r)+sqrt(r2-q3));
         double v = u == 0 ? 0 : q/u;
         x.t0 = (u+v)-a;
         if (u == v || fabs(u-v) < 1e-12*fabs(u+v)) {
@@ -498,10 +503,17 @@ __device__ __forceinline__ SDist sd_linear(const SegRec &s, d2 p, double need) {
     return r;
 }
 
-__device__ __forceinline__ void quad_root(d2 qa, d2 ab, d2 br, double t, double &minDistance, bool &interior) {
+// One root of the foot-point cubic (edge-segments.cpp:209-216).  `unsure` is raised when the outcome hinges on the last bits of
+// the root: a root within 1e-9 of the ends of (0,1), or a distance within 1e-13 (relative) of the running minimum — the fast
+// path's polished roots are accurate to ~1e-14 but not bit-faithful, so such an edge is re-evaluated with the literal solver.
+__device__ __forceinline__ void quad_root(d2 qa, d2 ab, d2 br, double t, double &minDistance, bool &interior, bool &unsure) {
+    if (fabs(t) < 1e-9 || fabs(t-1) < 1e-9)
+        unsure = true;
     if (t > 0 && t < 1) {
         d2 qe = qa+(2*t)*ab+(t*t)*br;
         double distance = len(qe);
+        if (fabs(distance-fabs(minDistance)) <= 1e-13*distance)
+            unsure = true;
         if (distance <= fabs(minDistance)) {
             minDistance = signed_by(cross(ab+t*br, qe), distance);
             interior = true;
@@ -509,28 +521,8 @@ __device__ __forceinline__ void quad_root(d2 qa, d2 ab, d2 br, double t, double 
     }
 }
 
-__device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need) {
-    d2 qa = s.p0-p;
-    d2 ab = mk(s.e[0], s.e[1]);
-    d2 br = mk(s.e[2], s.e[3]);
-    double a = s.e[4];
-    double b = s.e[5];
-    double c = s.e[6]+dot(qa, br);
-    double d = dot(qa, ab);
-    Roots t;
-    if (s.flags&SEG_CUBIC_NORMED) {
-#if B200_EXACT_ROOTS
-        t = solve_cubic_normed(s.e[13], c/a, d/a);
-#else
-        bool ok = !(s.flags&SEG_EXACT_ROOTS);
-        if (ok)
-            t = solve_cubic_fast(s.e[13], c*s.p3.x, d*s.p3.x, ok);
-        if (!ok)
-            t = solve_cubic_normed(s.e[13], c/a, d/a);
-#endif
-    } else
-        t = solve_quadratic(b, c, d);
-
+// The part of QuadraticSegment::signedDistance that follows the root solve (edge-segments.cpp:198-226)
+__device__ __forceinline__ SDist quad_finish(const SegRec &s, d2 p, d2 qa, d2 ab, d2 br, const Roots &t, double need, bool &unsure) {
     d2 epDir = mk(s.e[7], s.e[8]);
     double lenA = len(qa);
     double minDistance = signed_by(cross(epDir, qa), lenA);
@@ -546,9 +538,9 @@ __device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need
         param.den = s.e[12];
     }
     bool interior = false;     // param became a root in (0,1)
-    if (t.n > 0) quad_root(qa, ab, br, t.t0, minDistance, interior);
-    if (t.n > 1) quad_root(qa, ab, br, t.t1, minDistance, interior);
-    if (t.n > 2) quad_root(qa, ab, br, t.t2, minDistance, interior);
+    if (t.n > 0) quad_root(qa, ab, br, t.t0, minDistance, interior, unsure);
+    if (t.n > 1) quad_root(qa, ab, br, t.t1, minDistance, interior, unsure);
+    if (t.n > 2) quad_root(qa, ab, br, t.t2, minDistance, interior, unsure);
 
     SDist r;
     r.d = minDistance;
@@ -564,6 +556,49 @@ __device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need
                 r.dot = fabs(dot(s.bDirNZ, normalize_known(qb, lenB)));
         }
     }
+    return r;
+}
+
+// (out of line: reached only through the guard band)
+__device__ __noinline__ SDist sd_quadratic_literal(const SegRec &s, d2 p, double need) {
+    d2 qa = s.p0-p;
+    d2 ab = mk(s.e[0], s.e[1]);
+    d2 br = mk(s.e[2], s.e[3]);
+    double a = s.e[4];
+    double c = s.e[6]+dot(qa, br);
+    double d = dot(qa, ab);
+    bool unsure = false;
+    Roots t = solve_cubic_normed(s.e[13], c/a, d/a);
+    return quad_finish(s, p, qa, ab, br, t, need, unsure);
+}
+
+__device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need) {
+    d2 qa = s.p0-p;
+    d2 ab = mk(s.e[0], s.e[1]);
+    d2 br = mk(s.e[2], s.e[3]);
+    double a = s.e[4];
+    double b = s.e[5];
+    double c = s.e[6]+dot(qa, br);
+    double d = dot(qa, ab);
+    Roots t;
+    bool fast = false;
+    if (s.flags&SEG_CUBIC_NORMED) {
+#if B200_EXACT_ROOTS
+        t = solve_cubic_normed(s.e[13], c/a, d/a);
+#else
+        bool ok = !(s.flags&SEG_EXACT_ROOTS);
+        if (ok)
+            t = solve_cubic_fast(s.e[13], c*s.p3.x, d*s.p3.x, ok);
+        fast = ok;
+        if (!ok)
+            t = solve_cubic_normed(s.e[13], c/a, d/a);
+#endif
+    } else
+        t = solve_quadratic(b, c, d);
+    bool unsure = false;
+    SDist r = quad_finish(s, p, qa, ab, br, t, need, unsure);
+    if (fast && unsure)
+        r = sd_quadratic_literal(s, p, need);
     return r;
 }
 

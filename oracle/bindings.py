@@ -257,6 +257,18 @@ class Oracle:
             raise RuntimeError("render_sdf: unsupported channel combination")
         return out
 
+    def estimate_sdf_error(self, sdf, cbegin, points, orders, xf, scanlines_per_row=4, fill_rule=0, shape_ydown=False):
+        """estimateSDFError of the compiled reference (core/sdf-error-estimation.h:19-21) for one [h,w,N] field."""
+        assert self.is_ref
+        sdf = np.ascontiguousarray(sdf, dtype=np.float32)
+        h, w, n = sdf.shape
+        cbegin, points, orders = _u32(cbegin), _f64(points), _u8(orders)
+        x = _f64(np.asarray(xf, dtype=np.float64)[:4])
+        fn = self.lib.ref_estimate_sdf_error
+        fn.restype = C.c_double
+        return float(fn(C.c_int(n), C.c_int(len(cbegin) - 1), _p(cbegin, C.c_uint32), _p(points, C.c_double), _p(orders, C.c_uint8),
+                        C.c_int(int(shape_ydown)), _p(x, C.c_double), _p(sdf, C.c_float), C.c_int(w), C.c_int(h), C.c_int(scanlines_per_row), C.c_int(fill_rule)))
+
     def simulate_8bit(self, bitmap):
         """simulate8bit (core/render-sdf.h:19-21) on a copy."""
         b = np.array(bitmap, dtype=np.float32, order="C", copy=True)

@@ -38,6 +38,7 @@
 #include "core/pixel-conversion.hpp"
 #include "core/equation-solver.h"
 #include "core/render-sdf.h"
+#include "core/sdf-error-estimation.h"
 
 using namespace msdfgen;
 
@@ -357,6 +358,20 @@ int ref_render_sdf(int outN, float *out, int ow, int oh, int sdfN, const float *
 }
 
 /// simulate8bit (core/render-sdf.h:19-21), in place on n floats.
+/// estimateSDFError(sdf, shape, projection, scanlinesPerRow, fillRule)  (core/sdf-error-estimation.h:19-21); xf: scale, translate
+double ref_estimate_sdf_error(int N, int nContours, const uint32_t *cbegin, const double *points, const uint8_t *orders, int yDown,
+                              const double *xf, const float *sdf, int w, int h, int scanlinesPerRow, int fillRule) {
+    Shape shape;
+    buildShape(shape, nContours, cbegin, points, orders, NULL, yDown);
+    Projection projection(Vector2(xf[0], xf[1]), Vector2(xf[2], xf[3]));
+    switch (N) {
+        case 1: return estimateSDFError(BitmapConstSection<float, 1>(sdf, w, h), shape, projection, scanlinesPerRow, (FillRule) fillRule);
+        case 3: return estimateSDFError(BitmapConstSection<float, 3>(sdf, w, h), shape, projection, scanlinesPerRow, (FillRule) fillRule);
+        case 4: return estimateSDFError(BitmapConstSection<float, 4>(sdf, w, h), shape, projection, scanlinesPerRow, (FillRule) fillRule);
+    }
+    return -1;
+}
+
 void ref_simulate_8bit(float *pixels, int w, int h, int N) {
     if (N == 1) simulate8bit(BitmapSection<float, 1>(pixels, w, h));
     else if (N == 3) simulate8bit(BitmapSection<float, 3>(pixels, w, h));

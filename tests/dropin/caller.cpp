@@ -7,6 +7,8 @@
 
 #include <cstdint>
 #include <cstring>
+#include <thread>
+#include <vector>
 
 using namespace msdfgen;
 
@@ -133,6 +135,41 @@ int caller_render(int nContours, const uint32_t *cbegin, const double *pts, cons
     generateMTSDF(mtsdf, shape, t);
     renderSDF(BitmapSection<float, 1>(out+size_t(2*w)*(2*h)*3, w, h), mtsdf);
     return 0;
+}
+
+
+// Re-entrancy (the reference's generators are free functions without shared state, msdfgen.h:47-69): nThreads host threads
+// generate concurrently, each its own Shape object and its own bitmap of its own size (w+thread, h+thread), `reps` times.
+// out: the threads' [h+t][w+t][3] images back to back.  Returns the number of generator calls made.
+int caller_threads(int nThreads, int reps, int nContours, const uint32_t *cbegin, const double *pts, const uint8_t *orders, int w, int h, float *out) {
+    std::vector<std::thread> threads;
+    std::vector<size_t> offsets;
+    size_t off = 0;
+    for (int t = 0; t < nThreads; ++t) {
+        offsets.push_back(off);
+        off += size_t(w+t)*(h+t)*3;
+    }
+    std::vector<int> calls((size_t) nThreads, 0);
+    for (int t = 0; t < nThreads; ++t)
+        threads.push_back(std::thread([=, &calls]() {
+            Shape shape;
+            buildShape(shape, nContours, cbegin, pts, orders, 0);
+            shape.normalize();
+            edgeColoringSimple(shape, 3.0, (unsigned long long) t);
+            const int tw = w+t, th = h+t;
+            Bitmap<float, 3> msdf(tw, th);
+            for (int r = 0; r < reps; ++r) {
+                generateMSDF(msdf, shape, autoframe(shape, tw, th, 4.0));
+                ++calls[(size_t) t];
+            }
+            memcpy(out+offsets[(size_t) t], (const float *) msdf, size_t(tw)*th*3*sizeof(float));
+        }));
+    int total = 0;
+    for (int t = 0; t < nThreads; ++t) {
+        threads[(size_t) t].join();
+        total += calls[(size_t) t];
+    }
+    return total;
 }
 
 }

@@ -20,6 +20,9 @@ for i, seed in enumerate(seeds):
     arrays[f"edges{i}"] = np.int64(r["edges"])
     for key in ("msdf", "modes", "ec", "stencil", "scanline", "render"):
         arrays[f"{key}{i}"] = r[key]
+# caller_threads: four threads, sizes (24+t) x (20+t), colouring seed t — the reference's images for the re-entrancy test
+for t, img in enumerate(test_dropin._threads(lib, synth_glyph(321, cubic_fraction=0.2), 4, 1)):
+    arrays[f"threads{t}"] = img
 path = os.path.join(ROOT, "tests", "golden", "dropin_v1.npz")
 np.savez_compressed(path, **arrays)
 print(path, os.path.getsize(path) // 1024, "KiB")

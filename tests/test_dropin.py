@@ -25,7 +25,7 @@ def _build_ref():
     lib = os.path.join(OUT, "libcaller_ref.so")
     if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(SRC):
         core = sorted(os.path.join(REF, "core", f) for f in os.listdir(os.path.join(REF, "core")) if f.endswith(".cpp"))
-        subprocess.run([CXX, "-O2", "-ffp-contract=off", "-std=c++11", "-fPIC", "-shared", "-DMSDFGEN_PUBLIC=", "-DMSDFGEN_USE_CPP11",
+        subprocess.run([CXX, "-O2", "-ffp-contract=off", "-std=c++11", "-pthread", "-fPIC", "-shared", "-DMSDFGEN_PUBLIC=", "-DMSDFGEN_USE_CPP11",
                         f"-I{REF}", "-o", lib, SRC] + core, check=True, capture_output=True)
     return C.CDLL(lib)
 
@@ -36,7 +36,7 @@ def _build_b200():
     host = os.path.join(ROOT, "msdfgen_b200")
     deps = [SRC, os.path.join(host, "host", "msdfgen.h"), os.path.join(host, "libmsdfgen_b200_host.so")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
-        subprocess.run([CXX, "-O2", "-ffp-contract=off", "-std=c++11", "-fPIC", "-shared", f"-I{host}/host", "-o", lib, SRC,
+        subprocess.run([CXX, "-O2", "-ffp-contract=off", "-std=c++11", "-pthread", "-fPIC", "-shared", f"-I{host}/host", "-o", lib, SRC,
                         f"-L{host}", "-lmsdfgen_b200_host", "-lmsdfgen_b200", f"-Wl,-rpath,{host}"], check=True, capture_output=True)
     return C.CDLL(lib)
 
@@ -96,3 +96,78 @@ def test_b200_build_matches_reference_build():
             assert over == 0 and max_abs <= 1e-4, (key, seed, bits, max_abs)
             assert np.array_equal(to_bytes(mine[key]), to_bytes(want))
         assert np.array_equal(mine["stencil"], z[f"stencil{i}"])
+
+
+def _threads(lib, g, n_threads, reps, w=24, h=20):
+    sizes = [(w + t, h + t) for t in range(n_threads)]
+    out = np.full(sum(a * b * 3 for a, b in sizes), np.nan, np.float32)
+    calls = lib.caller_threads(C.c_int(n_threads), C.c_int(reps), *_args(g), C.c_int(w), C.c_int(h), out.ctypes.data_as(C.POINTER(C.c_float)))
+    assert calls == n_threads * reps
+    imgs, off = [], 0
+    for a, b in sizes:
+        imgs.append(out[off:off + a * b * 3].reshape(b, a, 3))
+        off += a * b * 3
+    return imgs
+
+
+def test_reference_build_is_reentrant(ref):
+    """The contract the mirror has to keep: concurrent generator calls from several host threads give what sequential calls give."""
+    lib = _build_ref()
+    g = synth_glyph(321, cubic_fraction=0.2)
+    seq = [_threads(lib, g, t + 1, 1)[t] for t in range(4)]
+    par = _threads(lib, g, 4, 3)
+    for a, b in zip(seq, par):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_b200_build_is_reentrant_and_matches_reference():
+    """Four host threads call msdfgen::generateMSDF concurrently through the C++ mirror (one context per calling thread, each
+    with its own stream): the images equal the single-threaded ones and the reference's."""
+    b200 = _build_b200()
+    g = synth_glyph(321, cubic_fraction=0.2)
+    seq = [_threads(b200, g, t + 1, 1)[t] for t in range(4)]
+    for rep in range(3):
+        par = _threads(b200, g, 4, 8)
+        for a, b in zip(seq, par):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dropin_v1.npz"))
+    for t in range(4):
+        want = z[f"threads{t}"]
+        bits, max_abs, over = compare(seq[t], want)
+        assert over == 0 and max_abs <= 1e-4 and np.array_equal(to_bytes(seq[t]), to_bytes(want)), (t, bits, max_abs)
+
+
+@pytest.mark.gpu
+def test_two_threads_share_one_context_serialised(ctx):
+    """A context is not internally locked (include/msdfgen_b200.h: one per thread); two threads may still share one if the caller
+    serialises the calls — e.g. a worker pool around one GPU.  ctypes releases the GIL during the calls, so the lock is real."""
+    import threading
+    from msdfgen_b200 import api, prep
+    from msdfgen_b200.synth import synth_atlas, glyph_transform
+    atlases = [prep.prepare(synth_atlas(64, seed=500 + i)) for i in range(2)]
+    xf = glyph_transform(32)
+    want = []
+    for a in atlases:
+        o = np.empty((64, 32, 32, 3), np.float32)
+        ctx.generate_batch(api.MSDF, o, a, xf)
+        want.append(o)
+    lock = threading.Lock()
+    got = [np.empty((64, 32, 32, 3), np.float32) for _ in range(2)]
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(10):
+                with lock:
+                    ctx.generate_batch(api.MSDF, got[i], atlases[i], xf)
+                if not np.array_equal(got[i].view(np.uint32), want[i].view(np.uint32)):
+                    errors.append(i)
+        except Exception as e:          # noqa: BLE001
+            errors.append(repr(e))
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors

@@ -11,7 +11,8 @@ from util import fuzz_shape, fuzz_configs, digest
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_v1.json")))
 SEEDS = range(108)
-HAIRPIN = 8      # fuzz family (cusps) whose result at the cusp is libm rounding noise in the reference (tests/util.py)
+HAIRPIN = 8      # fuzz family (quadratic cusps): the reference's texels at a cusp hinge on the last bit of libm's acos / cos / pow;
+                 # the device's literal solver uses correctly rounded versions (csrc/cr_math.cuh) and is held to the same digests
 
 
 def test_port_matches_reference_digests(port):
@@ -51,15 +52,6 @@ def test_cuda_matches_reference_digests(ctx, port):
             cfg = api.MSDFGeneratorConfig(overlapSupport=ocfg.overlap, errorCorrection=api.ErrorCorrectionConfig(mode=ocfg.ec_mode, distanceCheckMode=ocfg.ec_dcm))
             f = np.full((h, w, api.CHANNELS[MODE[mode]]), np.nan, np.float32)
             ctx.generate(MODE[mode], f, shape, xf, cfg)
-            if fam == HAIRPIN:
-                # magnitudes only, and only where the sign is the whole story (true distance, no error correction)
-                want = port.generate(mode, cb, pts, od, cl, xf, w, h, ocfg)
-                if mode == "sdf" and not np.allclose(np.abs(f - 0.5), np.abs(want - 0.5), rtol=0, atol=1e-6):
-                    bad.append((seed, fam, key, "magnitude"))
-                # a channel without edges is -inf in both (error correction may then replace noise-dependent texels by the median)
-                if key.endswith("ec0") and not np.array_equal(np.isfinite(f), np.isfinite(want)):
-                    bad.append((seed, fam, key, "non-finite"))
-                continue
             if digest(f) != GOLDEN[f"{seed}/{key}"]:
                 want = port.generate(mode, cb, pts, od, cl, xf, w, h, ocfg)
                 bad.append((seed, fam, key, int((f.view(np.uint32) != want.view(np.uint32)).sum()), float(np.nanmax(np.abs(f - want)))))
@@ -74,3 +66,24 @@ def test_cuda_matches_reference_digests(ctx, port):
         if digest(r) != GOLDEN[f"{seed}/raster"]:
             bad.append((seed, fam, "raster"))
     assert not bad, (len(bad), bad[:12])
+
+
+@pytest.mark.gpu
+def test_literal_solver_is_rare_on_ordinary_glyphs_and_used_on_cusps(ctx):
+    """The fast foot-point root path falls back to the literal (correctly rounded) solver only inside its guard band: a tiny
+    fraction of the edge evaluations of ordinary glyphs.  Cusp segments always take the literal solver."""
+    from msdfgen_b200 import api, prep
+    from msdfgen_b200.flat import FlatShapes
+    from msdfgen_b200.synth import synth_atlas, glyph_transform
+    atlas = prep.prepare(synth_atlas(256, seed=31337))
+    out = np.empty((256, 32, 32, 3), np.float32)
+    ctx.exact_root_calls(reset=True)
+    ctx.generate_batch(api.MSDF, out, atlas, glyph_transform(32))
+    ordinary = ctx.exact_root_calls(reset=True)
+    quadratic_evals_at_least = 256 * 32 * 32          # every texel evaluates at least one quadratic edge of these glyphs, typically several
+    print(f"[guard band] literal-solver runs on 256 ordinary glyphs: {ordinary} ({ordinary / quadratic_evals_at_least:.2e} per texel)")
+    assert ordinary < 0.01 * quadratic_evals_at_least
+    fam, cb, pts, od, cl, xf, w, h = fuzz_shape(HAIRPIN)
+    f = np.empty((h, w, 1), np.float32)
+    ctx.generate(api.SDF, f, FlatShapes.single(cb, pts, od, cl), xf)
+    assert ctx.exact_root_calls(reset=True) > 0
