@@ -216,7 +216,8 @@ int b200msdf_batch_upload_regions(b200msdf_ctx *ctx, int mode, const b200msdf_sh
 /* Enqueues the whole path (contour windings -> distance field -> error correction) for the batch. */
 int b200msdf_batch_launch(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200msdf_config *config);
 /* Same, restricted to some stages (for per-kernel timing): bit 0 windings/prepare, bit 1 distance field, bit 2 error correction,
- * bit 3 scanline pass (only when config->scanline_pass).
+ * bit 3 scanline pass (only when config->scanline_pass), bits 4 / 5 the two kernels of the distance field one at a time (k1a_filter /
+ * k1b_exact; small glyphs only).
  * Later stages read what earlier stages of a previous full launch left in HBM. */
 int b200msdf_batch_launch_stages(b200msdf_ctx *ctx, b200msdf_batch *batch, const b200msdf_config *config, unsigned stages);
 /* Sign-corrects the batch's most recent result in place on the device (after stages 1|2 it is the raw field, after a full

@@ -120,7 +120,8 @@ struct b200msdf_batch {
     DevBuf blocks, blockWork;     // big shapes: 2-D block tiles of k1_big_blocks and its per-CTA list / cap workspace
     int nBlocks = 0, maxBigSegs = 0, maxBigContours = 0;
     std::vector<TileDesc> hBlocks;
-    DevBuf k1Counters;            // one tile counter per k1a / k1b launch of a round
+    DevBuf k1Counters;            // one tile counter per k1a / k1b launch of a round (+ the recheck launch)
+    DevBuf recheck;               // guard-band texel mask + tile flags
     DevBuf filt, tileFilt;        // k1a -> k1b filter words (sized at launch) and the small tiles' word offsets: [overlap][tile], [simple][tile]
     size_t filtWords[2] = { 0, 0 };
     std::vector<unsigned long long> hTileFilt;
@@ -132,7 +133,7 @@ struct b200msdf_batch {
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
         bigGlyphs.release(); bigRecs.release(); bigCull.release(); bigPerp.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); scratchW.release(); bytes.release(); byteTargets.release(); signMatch.release();
-        blocks.release(); blockWork.release(); filt.release(); tileFilt.release(); k1Counters.release();
+        blocks.release(); blockWork.release(); filt.release(); tileFilt.release(); k1Counters.release(); recheck.release();
     }
 };
 
@@ -144,6 +145,7 @@ struct b200msdf_ctx {
     PinBuf pinOut, pinIn, pinDesc;  // pinDesc: staging of per-batch descriptors (glyphs, tiles) so that their H2D copies are true async DMAs
     cudaEvent_t descDone = nullptr; // the last copy out of pinDesc
     uint64_t launches = 0;
+    unsigned k1Parts = 3;           // per-kernel timing (b200msdf_batch_launch_stages): bit 0 k1a_filter, bit 1 k1b_exact + recheck
     // resident CTAs per SM of every kernel launched through this context, and the dynamic-shared-memory opt-in that goes with
     // it: both are per DEVICE, and a context is bound to one device
     std::unordered_map<const void *, int> occupancy;
@@ -482,8 +484,15 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
             if (w > roundWords) roundWords = w;
         }
         if ((rc = bb->filt.reserve(roundWords*sizeof(unsigned)+256))) return rc;
-        if ((rc = bb->k1Counters.reserve(sizeof(int)*2*(size_t) rounds))) return rc;
-        CUDA_TRY(cudaMemsetAsync(bb->k1Counters.p, 0, sizeof(int)*2*(size_t) rounds, ctx->stream));
+        if ((rc = bb->k1Counters.reserve(sizeof(int)*(2*(size_t) rounds+1)))) return rc;
+        CUDA_TRY(cudaMemsetAsync(bb->k1Counters.p, 0, sizeof(int)*(2*(size_t) rounds+1), ctx->stream));
+        // guard band of the fast foot-point roots: k1b flags the texels (and tiles) whose outcome hinged on the last bits of a root
+        const size_t maskBytes = ((bb->texels+31)/32)*4, tileBytes = ((size_t) P.nSmallTiles+3)&~size_t(3);
+        if ((rc = bb->recheck.reserve(maskBytes+tileBytes+16))) return rc;
+        CUDA_TRY(cudaMemsetAsync(bb->recheck.p, 0, maskBytes+tileBytes+4, ctx->stream));
+        P.recheckMask = bb->recheck.as<unsigned>();
+        P.recheckTiles = bb->recheck.as<unsigned char>()+maskBytes;
+        P.recheckAny = reinterpret_cast<int *>(bb->recheck.as<unsigned char>()+maskBytes+tileBytes);
         int *const batchCounters = P.counters;
         P.counters = bb->k1Counters.as<int>();
         for (int r = 0; r < rounds && !rc; ++r) {
@@ -491,10 +500,14 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
             P.tileEnd = P.tileBegin+roundTiles < P.nSmallTiles ? P.tileBegin+roundTiles : P.nSmallTiles;
             P.counterIndex = 2*r;
             P.filt = bb->filt.as<unsigned>()-hOff[P.tileBegin];       // tileFilt offsets are batch-wide; the round starts at 0
-            rc = launch_tiles(ctx, k1a_filter<MODE, OVERLAP>, P, 0, 0, K1_THREADS);
+            if (ctx->k1Parts&1u)
+                rc = launch_tiles(ctx, k1a_filter<MODE, OVERLAP>, P, 0, 0, K1_THREADS);
             P.counterIndex = 2*r+1;
-            if (!rc) rc = launch_tiles(ctx, k1b_exact<MODE, OVERLAP>, P, scratch, 0, K1_THREADS);
+            if (!rc && (ctx->k1Parts&2u)) rc = launch_tiles(ctx, k1b_exact<MODE, OVERLAP>, P, scratch, 0, K1_THREADS);
         }
+        // ... and the flagged texels are recomputed with the literal solver (a handful per atlas; tiles without any are skipped)
+        P.tileBegin = 0; P.tileEnd = P.nSmallTiles; P.counterIndex = 2*rounds;
+        if (!rc && (ctx->k1Parts&2u)) rc = launch_tiles(ctx, k1_distance_field<MODE, OVERLAP, true>, P, scratch);
         P.counters = batchCounters;
         P.tileBegin = 0; P.tileEnd = P.nSmallTiles; P.counterIndex = 0;
         if (rc) return rc;
@@ -696,8 +709,13 @@ int launch_batch(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
         // the tile counters are normally reset by the prologue kernel
         CUDA_TRY(cudaMemsetAsync(P.counters, 0, 8*sizeof(int), ctx->stream));
     }
-    if (stages&2u)
-        if ((rc = launch_k1(ctx, b->mode, cfg->overlap_support != 0, P, b->maxContours))) return rc;
+    if (stages&(2u|16u|32u)) {
+        // stage bits 16 / 32: only k1a_filter / only k1b_exact (the latter reads the words a previous launch left) — kernel timing
+        ctx->k1Parts = (stages&2u) ? 3u : ((stages&16u) ? 1u : 0u)|((stages&32u) ? 2u : 0u);
+        rc = launch_k1(ctx, b->mode, cfg->overlap_support != 0, P, b->maxContours);
+        ctx->k1Parts = 3u;
+        if (rc) return rc;
+    }
     b->current = P.field;
     if (scan && (stages&8u))
         if ((rc = launch_sign(ctx, b, P, P.field, ec ? P.field : finalOut, cfg->sdf_zero_value, cfg->fill_rule))) return rc;

@@ -506,14 +506,21 @@ __device__ __forceinline__ SDist sd_linear(const SegRec &s, d2 p, double need) {
 // One root of the foot-point cubic (edge-segments.cpp:209-216).  `unsure` is raised when the outcome hinges on the last bits of
 // the root: a root within 1e-9 of the ends of (0,1), or a distance within 1e-13 (relative) of the running minimum — the fast
 // path's polished roots are accurate to ~1e-14 but not bit-faithful, so such an edge is re-evaluated with the literal solver.
+#ifndef B200_GUARD_BAND
+#define B200_GUARD_BAND 1
+#endif
 __device__ __forceinline__ void quad_root(d2 qa, d2 ab, d2 br, double t, double &minDistance, bool &interior, bool &unsure) {
+#if B200_GUARD_BAND
     if (fabs(t) < 1e-9 || fabs(t-1) < 1e-9)
         unsure = true;
+#endif
     if (t > 0 && t < 1) {
         d2 qe = qa+(2*t)*ab+(t*t)*br;
         double distance = len(qe);
+#if B200_GUARD_BAND
         if (fabs(distance-fabs(minDistance)) <= 1e-13*distance)
             unsure = true;
+#endif
         if (distance <= fabs(minDistance)) {
             minDistance = signed_by(cross(ab+t*br, qe), distance);
             interior = true;
@@ -559,19 +566,16 @@ __device__ __forceinline__ SDist quad_finish(const SegRec &s, d2 p, d2 qa, d2 ab
     return r;
 }
 
-// (out of line: reached only through the guard band)
-__device__ __noinline__ SDist sd_quadratic_literal(const SegRec &s, d2 p, double need) {
-    d2 qa = s.p0-p;
-    d2 ab = mk(s.e[0], s.e[1]);
-    d2 br = mk(s.e[2], s.e[3]);
-    double a = s.e[4];
-    double c = s.e[6]+dot(qa, br);
-    double d = dot(qa, ab);
-    bool unsure = false;
-    Roots t = solve_cubic_normed(s.e[13], c/a, d/a);
-    return quad_finish(s, p, qa, ab, br, t, need, unsure);
+// Per-thread flag in shared memory: set when the guard band of quad_root was hit during the thread's current texel.
+__device__ __forceinline__ unsigned char &guard_flag() {
+    __shared__ unsigned char s_guard[1024];
+    return s_guard[threadIdx.x];
 }
 
+// LITERAL = false: fast foot-point roots (fp32 closed form + fp64 polish); guard_flag() is raised when the guard band of
+// quad_root was hit — the caller then has the texel re-evaluated with LITERAL = true (k1b_exact -> k1_distance_field recheck
+// launch), which takes the reference's closed form with correctly rounded acos / cos / pow for every quadratic segment.
+template <bool LITERAL>
 __device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need) {
     d2 qa = s.p0-p;
     d2 ab = mk(s.e[0], s.e[1]);
@@ -583,22 +587,18 @@ __device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need
     Roots t;
     bool fast = false;
     if (s.flags&SEG_CUBIC_NORMED) {
-#if B200_EXACT_ROOTS
-        t = solve_cubic_normed(s.e[13], c/a, d/a);
-#else
-        bool ok = !(s.flags&SEG_EXACT_ROOTS);
+        bool ok = !LITERAL && !B200_EXACT_ROOTS && !(s.flags&SEG_EXACT_ROOTS);
         if (ok)
             t = solve_cubic_fast(s.e[13], c*s.p3.x, d*s.p3.x, ok);
         fast = ok;
         if (!ok)
             t = solve_cubic_normed(s.e[13], c/a, d/a);
-#endif
     } else
         t = solve_quadratic(b, c, d);
     bool unsure = false;
     SDist r = quad_finish(s, p, qa, ab, br, t, need, unsure);
     if (fast && unsure)
-        r = sd_quadratic_literal(s, p, need);
+        guard_flag() = 1;       // (a store on a rare path instead of a value carried through the callers' hot loops)
     return r;
 }
 
@@ -664,12 +664,13 @@ __device__ __noinline__ SDist sd_cubic(const SegRec &s, d2 p, double need) {
     return r;
 }
 
+template <bool LITERAL = false>
 __device__ __forceinline__ SDist signed_distance(const SegRec &s, d2 p, double need) {
     // s.order is uniform across the CTA (every thread walks the same record), so this switch does not diverge
     if (s.order == 1)
         return sd_linear(s, p, need);
     if (s.order == 2)
-        return sd_quadratic(s, p, need);
+        return sd_quadratic<LITERAL>(s, p, need);
     return sd_cubic(s, p, need);
 }
 
@@ -787,7 +788,7 @@ __device__ __forceinline__ void sel_distance(const Sel<MODE> &s, const SegRec *r
 //     other |pd| is irrelevant by the previous sentence.
 // The result is bit-identical to evaluating every edge (the reference's EdgeCache prunes on the same principle, using
 // the previous pixel's distances instead of a bounding circle).
-template <int MODE>
+template <int MODE, bool LITERAL = false>
 __device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, int recIndex, d2 p, double *lim) {
     // lim[k] = min(cap[k], |current minimum of channel k|), kept up to date by this function; mask is uniform across the
     // warp (every thread walks the same record), so the branches below do not diverge
@@ -803,7 +804,7 @@ __device__ __forceinline__ void sel_add_edge(Sel<MODE> &sel, const SegRec &s, in
     const bool culled = dsq > reach*reach*(1+1e-9);
     double rd = 0;
     if (!culled) {
-        SDist r = signed_distance(s, p, need);
+        SDist r = signed_distance<LITERAL>(s, p, need);
         rd = r.d;
         if (fabs(r.d) <= need) {
             int near = (recIndex<<2)|r.side;
@@ -1027,7 +1028,7 @@ __device__ __forceinline__ void combine_overlapping(const SegRec *recs, d2 p, Co
 // ShapeDistanceFinder<Combiner<Selector>>::oneShotDistance at point p over the glyph's records [0, nRec).
 // recs is shared memory (small glyphs) or the global prepared buffer (big shapes); every thread of the CTA walks the same
 // record at the same time, so loads broadcast.  out gets NOUT raw (unmapped) fp64 distances.
-template <int MODE, bool OVERLAP, typename IT>
+template <int MODE, bool OVERLAP, typename IT, bool LITERAL = false>
 __device__ __forceinline__ void shape_distance_over(const SegRec *recs, int nRec, IT it, d2 p, ContourStore store, double *out) {
     const int NOUT = ModeTraits<MODE>::NOUT;
     typedef StoreLayout<MODE> L;
@@ -1038,7 +1039,7 @@ __device__ __forceinline__ void shape_distance_over(const SegRec *recs, int nRec
         distance_caps<MODE>(recs, it, 0, nRec-1, p, cap);
         for (int i = 0; i < nRec; ++i) {
             const int j = it.at(i);
-            sel_add_edge<MODE>(sel, recs[j], j, p, cap);
+            sel_add_edge<MODE, LITERAL>(sel, recs[j], j, p, cap);
         }
         sel_distance<MODE>(sel, recs, p, out);
     } else {
@@ -1055,7 +1056,7 @@ __device__ __forceinline__ void shape_distance_over(const SegRec *recs, int nRec
                 distance_caps<MODE>(recs, it, j0, j1, p, cap);
                 for (int i = j0; i <= j1; ++i) {
                     const int j = it.at(i);
-                    sel_add_edge<MODE>(cur, recs[j], j, p, cap);
+                    sel_add_edge<MODE, LITERAL>(cur, recs[j], j, p, cap);
                 }
                 double cd[NOUT];
                 sel_distance<MODE>(cur, recs, p, cd);
@@ -1266,9 +1267,9 @@ __device__ __forceinline__ void shape_distance_fold(const SegRec *recs, int nRec
     for (int k = 0; k < NOUT; ++k) out[k] = dist[k];
 }
 
-template <int MODE, bool OVERLAP>
+template <int MODE, bool OVERLAP, bool LITERAL = false>
 __device__ __forceinline__ void shape_distance(const SegRec *recs, int nRec, d2 p, ContourStore store, double *out) {
-    shape_distance_over<MODE, OVERLAP>(recs, nRec, SeqIter(), p, store, out);
+    shape_distance_over<MODE, OVERLAP, SeqIter, LITERAL>(recs, nRec, SeqIter(), p, store, out);
 }
 
 }  // namespace b200

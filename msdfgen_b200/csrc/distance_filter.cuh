@@ -376,6 +376,7 @@ __device__ __forceinline__ void combine_parked(ContourStore &st, int nc, double 
 
 // Pass 3 and the contour combiner at p: ShapeDistanceFinder<Combiner<Selector>>::oneShotDistance restricted to what the filter
 // kept.  in: the unit's word block offset by the lane.  Must be called by ALL 32 lanes of the warp (warp-wide votes inside).
+// guard_flag() tells afterwards whether the texel has to be re-evaluated with the literal root solver (sd_quadratic).
 template <int MODE, bool OVERLAP>
 __device__ __forceinline__ void exact_texel(const SegRec *recs, int nRec, const int *groupEnd, int nGroupsAll, const unsigned *in,
                                             d2 p, ContourStore store, double *out) {

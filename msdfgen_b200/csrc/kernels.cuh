@@ -58,6 +58,9 @@ struct KernelParams {
     double *scratch;              // per-thread contour-distance slices for many-contour shapes
     signed char *scratchW;        // k1_big_blocks: per-thread winding slices (same indexing)
     size_t scratchStride;         // = gridDim.x * CTA_THREADS
+    unsigned *recheckMask;        // k1b -> recheck launch: one bit per texel of the batch (guard band of the fast root path)
+    unsigned char *recheckTiles;  // one byte per small tile: the tile has such texels
+    int *recheckAny;              // any texel flagged at all (the recheck launch returns at once otherwise)
     unsigned *filt;               // k1a -> k1b: per-unit filter words (distance_filter.cuh)
     const unsigned long long *tileFilt;   // word offset of every small tile's first unit in filt
     // error correction config
@@ -161,10 +164,15 @@ __device__ __forceinline__ void store_tile(float *dst, const float *staged, int 
     }
 }
 
-// BIG = false: tiles of glyphs whose records are prepared into shared memory by the CTA (the compiler sees a __shared__
-// array: LDS).  BIG = true: tiles of shapes whose records were prepared into the global buffer by k0_prepare_big.
-template <int MODE, bool OVERLAP, bool BIG>
+// The full walk (every texel evaluates every record with the exact fp64 culling of sel_add_edge): the distance kernel of
+// round 1, kept for two jobs.  RECHECK = false: A/B baseline (B200MSDF_K1_LEGACY=1).  RECHECK = true: launched after k1b_exact
+// over the tiles it flagged, it recomputes — with the LITERAL root solver for every quadratic segment — exactly the texels
+// whose fast-path result hinged on the last bits of a root (guard band), and overwrites them.
+template <int MODE, bool OVERLAP, bool RECHECK>
 __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams P) {
+    const bool BIG = false;
+    if (RECHECK && !*P.recheckAny)
+        return;
     const int NOUT = ModeTraits<MODE>::NOUT;
     __shared__ SegRec s_recs[BIG ? 1 : SMEM_RECORDS];
     __shared__ __align__(16) double s_points[BIG ? 2 : SMEM_RECORDS*8];
@@ -186,6 +194,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
         int tile = s_tile;
         if (tile >= P.tileEnd)
             break;
+        if (RECHECK && !P.recheckTiles[tile])
+            continue;
         TileDesc td = P.tiles[tile];
         if ((int) td.glyph != stagedGlyph) {
             if (threadIdx.x == 0)
@@ -223,22 +233,35 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams
                 slot = (by*4+(lane>>3))*unsigned(w)+bx*8+(lane&7);
             }
             unsigned i = passBase+slot;
-            if (i < tileEnd) {
+            bool mine = i < tileEnd;
+            if (RECHECK && mine) {
+                const size_t t = size_t(s_g.texelOffset)+i;
+                mine = (P.recheckMask[t>>5]>>(t&31))&1u;
+            }
+            if (mine) {
                 int x = int(i%unsigned(w));
                 int yOut = int(i/unsigned(w));
                 int y = s_g.flip ? s_g.h-1-yOut : yOut;
                 // Projection::unproject(Point2(x+.5, y+.5))
                 d2 p = mk((s_g.x0+x+.5)/s_g.sx-s_g.tx, (s_g.y0+y+.5)/s_g.sy-s_g.ty);
                 double dist[NOUT];
-                shape_distance<MODE, OVERLAP>(recs, nRec, p, store, dist);
-                #pragma unroll
-                for (int k = 0; k < NOUT; ++k)
-                    s_out[slot*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));    // DistanceMapping::operator()
+                shape_distance<MODE, OVERLAP, RECHECK>(recs, nRec, p, store, dist);
+                if (RECHECK) {
+                    #pragma unroll
+                    for (int k = 0; k < NOUT; ++k)
+                        P.field[s_g.outOffset+size_t(i)*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));
+                } else {
+                    #pragma unroll
+                    for (int k = 0; k < NOUT; ++k)
+                        s_out[slot*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));    // DistanceMapping::operator()
+                }
             }
-            __syncthreads();
-            unsigned nPix = tileEnd-passBase < CTA_THREADS ? tileEnd-passBase : CTA_THREADS;
-            store_tile(P.field+s_g.outOffset+size_t(passBase)*NOUT, s_out, int(nPix)*NOUT);
-            __syncthreads();
+            if (!RECHECK) {
+                __syncthreads();
+                unsigned nPix = tileEnd-passBase < CTA_THREADS ? tileEnd-passBase : CTA_THREADS;
+                store_tile(P.field+s_g.outOffset+size_t(passBase)*NOUT, s_out, int(nPix)*NOUT);
+                __syncthreads();
+            }
         }
     }
 }
@@ -431,6 +454,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1B_MIN_CTAS) k1b_exact(KernelPara
         mbar_init(&s_mbar);
     double localStore[OVERLAP ? B200_LOCAL_CONTOURS*StoreLayout<MODE>::PER_CONTOUR : 1];
     const unsigned lane = threadIdx.x&31, warp = threadIdx.x>>5;
+    guard_flag() = 0;
     int stagedGlyph = -1;
     for (;;) {
         __syncthreads();        // every warp has left the previous tile
@@ -480,6 +504,16 @@ __global__ void __launch_bounds__(K1_THREADS, K1B_MIN_CTAS) k1b_exact(KernelPara
             const d2 p = texel_point(s_g, x, yOut);
             double dist[NOUT];
             exact_texel<MODE, OVERLAP>(s_recs, nRec, s_groupEnd, s_nGroups, tileWords+size_t(u)*words*32u+lane, p, store, dist);
+            const bool unsure = guard_flag() != 0;
+            if (unsure)
+                guard_flag() = 0;
+            if (unsure && valid) {
+                // guard band hit: the recheck launch (k1_distance_field<.., LITERAL>) recomputes this texel with the literal solver
+                const size_t t = size_t(s_g.texelOffset)+size_t(yOut)*w+x;
+                atomicOr(&P.recheckMask[t>>5], 1u<<(t&31));
+                P.recheckTiles[tile] = 1;
+                *P.recheckAny = 1;
+            }
             if (valid) {
                 #pragma unroll
                 for (int k = 0; k < NOUT; ++k)

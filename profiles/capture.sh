@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 B="python bench.py --no-cpu-baseline --no-extras"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}.csv \
     $B --steps 2 --warmup 3 > gpurun_out/bench_under_ncu_${tag}.log 2>&1
-for k in k1_distance_field k2_classify k3_exact_distance; do
+for k in k1a_filter k1b_exact k2_classify k3_exact_distance; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -o gpurun_out/${k}_${tag} \
       $B --steps 1 --warmup 3 > gpurun_out/ncu_${k}_${tag}.log 2>&1
 done

@@ -24,7 +24,7 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__sass_branch_targets_threads_divergent.sum", "smsp__sass_branch_targets.sum"]
 
 traffic = {}
-for kernel in ("k1_distance_field", "k2_classify", "k3_exact_distance", "k1_big_blocks"):
+for kernel in ("k1a_filter", "k1b_exact", "k2_classify", "k3_exact_distance", "k1_big_blocks"):
     rep = os.path.join(ROOT, "gpurun_out", f"{kernel}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         continue
