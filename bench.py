@@ -121,7 +121,7 @@ class ClockSampler:
         # 0.25 s around it (the GPU is under the same load during warm-up and the stage timing that follow immediately)
         inside = [t for t, _ in self.rows if t0 - 0.05 <= t <= t1 + 0.05]
         pad = 0.05 if inside else 0.25
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for t, line in self.rows:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
@@ -129,6 +129,7 @@ class ClockSampler:
             try:
                 if t0 - pad <= t <= t1 + pad:
                     sm.append(float(f[0]))
+                    pw.append(float(f[2]))
                 mx.append(float(f[1]))
             except ValueError:
                 continue
@@ -138,7 +139,8 @@ class ClockSampler:
                         reasons.add(name)
         if not mx:
             return None
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons),
+                "power_w": float(np.median(pw)) if pw else None}
 
 
 # ======================================================================================================================
@@ -311,6 +313,12 @@ class Rig:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather(self, obj):
+        """[obj of rank 0, obj of rank 1, ...] on every rank."""
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
     def sum_over_ranks(self, x):
         if self.world == 1:
             return x
@@ -425,6 +433,7 @@ def run_atlas(rig, name, cfg, scaling, steps, warmup, atlas, xf, full=False):
                            "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_dom,
                            "kernel_ms": {"k0_windings": 1e3 * t_k0, "k1_distance_field": 1e3 * t_k1, "k1a_filter": 1e3 * t_k1a, "k1b_exact": 1e3 * t_k1b,
                                          "k2_error_correction": 1e3 * t_k2},
+                           "kernel_ms_per_rank": rig.gather([round(1e3 * t_k1, 4), round(1e3 * t_k2, 4)]) if rig.world > 1 else None,
                            "note": "fp64-ALU/latency bound by construction (thousands of fp64 ops per 13.5-byte texel, SURVEY.md §8d); "
                                    "see profiles/ for fp64-pipe utilisation and instruction counts"}
     batch.free()

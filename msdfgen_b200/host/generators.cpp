@@ -395,6 +395,35 @@ void distanceSignCorrection(const BitmapSection<float, 1> &sdf, const Shape &sha
 void distanceSignCorrection(const BitmapSection<float, 3> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule) { signCorrectOne(sdf, shape, Projection(scale, translate), .5f, fillRule); }
 void distanceSignCorrection(const BitmapSection<float, 4> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule) { signCorrectOne(sdf, shape, Projection(scale, translate), .5f, fillRule); }
 
+// ---- error estimation ------------------------------------------------------------------------------------------------------
+
+template <int N>
+double estimateOne(const BitmapConstSection<float, N> &sdf, const Shape &shape, const Projection &projection, int scanlinesPerRow, FillRule fillRule) {
+    b200msdf_ctx *ctx = context();
+    if (!ctx)
+        return 0;
+    FlatPool pool;
+    pool.add(shape);
+    b200msdf_shapes s = pool.view();
+    b200msdf_transform t = marshal(SDFTransformation(projection, Range(1)));
+    // (the reference reads the field's rows as they lie in memory: no reorientation of the section)
+    b200msdf_bitmap b;
+    b.pixels = const_cast<float *>(sdf.pixels);
+    b.width = sdf.width; b.height = sdf.height; b.row_stride = (int32_t) sdf.rowStride; b.y_downward = 0;
+    double error = 0;
+    int rc = b200msdf_estimate_sdf_error(ctx, N, &s, &t, 0, &b, scanlinesPerRow, (int) fillRule, &error);
+    if (rc)
+        report(rc);
+    return error;
+}
+
+double estimateSDFError(const BitmapConstSection<float, 1> &sdf, const Shape &shape, const Projection &projection, int scanlinesPerRow, FillRule fillRule) { return estimateOne(sdf, shape, projection, scanlinesPerRow, fillRule); }
+double estimateSDFError(const BitmapConstSection<float, 3> &sdf, const Shape &shape, const Projection &projection, int scanlinesPerRow, FillRule fillRule) { return estimateOne(sdf, shape, projection, scanlinesPerRow, fillRule); }
+double estimateSDFError(const BitmapConstSection<float, 4> &sdf, const Shape &shape, const Projection &projection, int scanlinesPerRow, FillRule fillRule) { return estimateOne(sdf, shape, projection, scanlinesPerRow, fillRule); }
+double estimateSDFError(const BitmapConstSection<float, 1> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, int scanlinesPerRow, FillRule fillRule) { return estimateOne(sdf, shape, Projection(scale, translate), scanlinesPerRow, fillRule); }
+double estimateSDFError(const BitmapConstSection<float, 3> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, int scanlinesPerRow, FillRule fillRule) { return estimateOne(sdf, shape, Projection(scale, translate), scanlinesPerRow, fillRule); }
+double estimateSDFError(const BitmapConstSection<float, 4> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, int scanlinesPerRow, FillRule fillRule) { return estimateOne(sdf, shape, Projection(scale, translate), scanlinesPerRow, fillRule); }
+
 // ---- preview rendering -----------------------------------------------------------------------------------------------------
 
 void renderSDF(const BitmapSection<float, 1> &output, const BitmapConstSection<float, 1> &sdf, Range sdfPxRange, float sdThreshold) { renderOne(output, sdf, sdfPxRange, sdThreshold); }

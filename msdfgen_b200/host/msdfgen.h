@@ -13,7 +13,8 @@
 //   bitmaps          core/BitmapRef.hpp, Bitmap.h, YAxisOrientation.h, pixel-conversion.hpp
 //   shape model      core/EdgeColor.h, edge-segments.h, EdgeHolder.h, Contour.h, Shape.h, edge-coloring.h
 //   generators       msdfgen.h:47-69, core/generator-config.h, core/msdf-error-correction.h
-// Out of scope: scanline rasterisation, Shape::orientContours, *_legacy generators, file I/O, SVG/FreeType import.
+// Out of scope: the host-side Scanline class and its users (Shape::scanline, scanlineSDF, Shape::orientContours), the
+// equation solvers as a public API, *_legacy generators, file I/O, SVG/FreeType import.
 #pragma once
 
 #include <cmath>
@@ -304,47 +305,13 @@ inline void interpolate(T *output, const BitmapConstSection<T, N> &bitmap, Point
         output[i] = mix(mix(bitmap(l, b)[i], bitmap(r, b)[i], lr), mix(bitmap(l, t)[i], bitmap(r, t)[i], lr), bt);
 }
 
-// ---- equation solvers (core/equation-solver.h) and scanlines (core/Scanline.h) ------------------------------------------------
-// ax^2 + bx + c = 0
-int solveQuadratic(double x[2], double a, double b, double c);
-// ax^3 + bx^2 + cx + d = 0
-int solveCubic(double x[3], double a, double b, double c, double d);
-
+// ---- fill rule (core/Scanline.h:9-14) ---------------------------------------------------------------------------------------
 /// Fill rule dictates how intersection total is interpreted during rasterization.
 enum FillRule {
     FILL_NONZERO,
     FILL_ODD, // "even-odd"
     FILL_POSITIVE,
     FILL_NEGATIVE
-};
-
-/// Resolves the number of intersection into a binary fill value based on fill rule.
-bool interpretFillRule(int intersections, FillRule fillRule);
-
-/// Represents a horizontal scanline intersecting a shape.
-class Scanline {
-public:
-    /// An intersection with the scanline: X coordinate, normalized Y direction of the oriented edge at the point of intersection.
-    struct Intersection {
-        double x;
-        int direction;
-    };
-    static double overlap(const Scanline &a, const Scanline &b, double xFrom, double xTo, FillRule fillRule);
-    Scanline();
-    /// Populates the intersection list.
-    void setIntersections(const std::vector<Intersection> &intersections);
-    void setIntersections(std::vector<Intersection> &&intersections);
-    /// Returns the number of intersections left of x.
-    int countIntersections(double x) const;
-    /// Returns the total sign of intersections left of x.
-    int sumIntersections(double x) const;
-    /// Decides whether the scanline is filled at x based on fill rule.
-    bool filled(double x, FillRule fillRule) const;
-private:
-    std::vector<Intersection> intersections;
-    mutable int lastIndex;
-    void preprocess();
-    int moveTo(double x) const;
 };
 
 // ---- shape model -------------------------------------------------------------------------------------------------------
@@ -365,8 +332,6 @@ public:
     virtual Point2 point(double param) const = 0;
     virtual Vector2 direction(double param) const = 0;
     virtual Vector2 directionChange(double param) const = 0;
-    /// Outputs a list of (at most three) intersections (their X coordinates) with an infinite horizontal scanline at y and returns how many there are.
-    virtual int scanlineIntersections(double x[3], int dy[3], double y) const = 0;
     virtual void bound(double &xMin, double &yMin, double &xMax, double &yMax) const = 0;
     virtual void reverse() = 0;
     virtual void moveStartPoint(Point2 to) = 0;
@@ -386,7 +351,6 @@ public:
     Vector2 direction(double param) const;
     Vector2 directionChange(double param) const;
     double length() const;
-    int scanlineIntersections(double x[3], int dy[3], double y) const;
     void bound(double &xMin, double &yMin, double &xMax, double &yMax) const;
     void reverse();
     void moveStartPoint(Point2 to);
@@ -406,7 +370,6 @@ public:
     Vector2 direction(double param) const;
     Vector2 directionChange(double param) const;
     double length() const;
-    int scanlineIntersections(double x[3], int dy[3], double y) const;
     void bound(double &xMin, double &yMin, double &xMax, double &yMax) const;
     void reverse();
     void moveStartPoint(Point2 to);
@@ -426,7 +389,6 @@ public:
     Point2 point(double param) const;
     Vector2 direction(double param) const;
     Vector2 directionChange(double param) const;
-    int scanlineIntersections(double x[3], int dy[3], double y) const;
     void bound(double &xMin, double &yMin, double &xMax, double &yMax) const;
     void reverse();
     void moveStartPoint(Point2 to);
@@ -490,11 +452,7 @@ public:
     void bound(double &xMin, double &yMin, double &xMax, double &yMax) const;
     void boundMiters(double &xMin, double &yMin, double &xMax, double &yMax, double border, double miterLimit, int polarity) const;
     Bounds getBounds(double border = 0, double miterLimit = 0, int polarity = 0) const;
-    /// Outputs the scanline that intersects the shape at y.
-    void scanline(Scanline &line, double y) const;
     int edgeCount() const;
-    /// Assumes its contours are unoriented (even-odd fill rule). Attempts to orient them to conform to the non-zero winding rule.
-    void orientContours();
     YAxisOrientation getYAxisOrientation() const;
     void setYAxisOrientation(YAxisOrientation yAxisOrientation);
 };
@@ -599,23 +557,13 @@ void simulate8bit(const BitmapSection<float, 1> &bitmap);
 void simulate8bit(const BitmapSection<float, 3> &bitmap);
 void simulate8bit(const BitmapSection<float, 4> &bitmap);
 
-// ---- error estimation (core/sdf-error-estimation.h); host code: a diagnostic, not part of the device path -----------------------
+// ---- error estimation (core/sdf-error-estimation.h:19-26): evaluated on the device (sdf_error.cuh) ---------------------------------
 
-/// Analytically constructs a scanline at y evaluating fill by linear interpolation of the SDF.
-void scanlineSDF(Scanline &line, const BitmapConstSection<float, 1> &sdf, const Projection &projection, double y, YAxisOrientation yAxisOrientation = MSDFGEN_Y_AXIS_DEFAULT_ORIENTATION);
-void scanlineSDF(Scanline &line, const BitmapConstSection<float, 3> &sdf, const Projection &projection, double y, YAxisOrientation yAxisOrientation = MSDFGEN_Y_AXIS_DEFAULT_ORIENTATION);
-void scanlineSDF(Scanline &line, const BitmapConstSection<float, 4> &sdf, const Projection &projection, double y, YAxisOrientation yAxisOrientation = MSDFGEN_Y_AXIS_DEFAULT_ORIENTATION);
 /// Estimates the portion of the area that will be filled incorrectly when rendering using the SDF.
 double estimateSDFError(const BitmapConstSection<float, 1> &sdf, const Shape &shape, const Projection &projection, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
 double estimateSDFError(const BitmapConstSection<float, 3> &sdf, const Shape &shape, const Projection &projection, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
 double estimateSDFError(const BitmapConstSection<float, 4> &sdf, const Shape &shape, const Projection &projection, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
 // Old version of the function API's kept for backwards compatibility
-void scanlineSDF(Scanline &line, const BitmapConstSection<float, 1> &sdf, const Projection &projection, double y, bool inverseYAxis);
-void scanlineSDF(Scanline &line, const BitmapConstSection<float, 3> &sdf, const Projection &projection, double y, bool inverseYAxis);
-void scanlineSDF(Scanline &line, const BitmapConstSection<float, 4> &sdf, const Projection &projection, double y, bool inverseYAxis);
-void scanlineSDF(Scanline &line, const BitmapConstSection<float, 1> &sdf, const Vector2 &scale, const Vector2 &translate, bool inverseYAxis, double y);
-void scanlineSDF(Scanline &line, const BitmapConstSection<float, 3> &sdf, const Vector2 &scale, const Vector2 &translate, bool inverseYAxis, double y);
-void scanlineSDF(Scanline &line, const BitmapConstSection<float, 4> &sdf, const Vector2 &scale, const Vector2 &translate, bool inverseYAxis, double y);
 double estimateSDFError(const BitmapConstSection<float, 1> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
 double estimateSDFError(const BitmapConstSection<float, 3> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
 double estimateSDFError(const BitmapConstSection<float, 4> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);

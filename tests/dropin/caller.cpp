@@ -138,6 +138,26 @@ int caller_render(int nContours, const uint32_t *cbegin, const double *pts, cons
 }
 
 
+// The command line's error estimate (main.cpp:1323-1379): generate, then estimateSDFError of the result.  out[0..2] = the estimates
+// of the sdf, msdf and mtsdf of the shape.
+int caller_estimate(int nContours, const uint32_t *cbegin, const double *pts, const uint8_t *orders, int w, int h, double *out) {
+    Shape shape;
+    buildShape(shape, nContours, cbegin, pts, orders, 0);
+    shape.normalize();
+    edgeColoringSimple(shape, 3.0);
+    SDFTransformation t = autoframe(shape, w, h, 4.0);
+    Bitmap<float, 1> sdf(w, h);
+    generateSDF(sdf, shape, t);
+    out[0] = estimateSDFError(sdf, shape, t, 4, FILL_NONZERO);
+    Bitmap<float, 3> msdf(w, h);
+    generateMSDF(msdf, shape, t);
+    out[1] = estimateSDFError(msdf, shape, t, 10, FILL_NONZERO);
+    Bitmap<float, 4> mtsdf(w, h);
+    generateMTSDF(mtsdf, shape, t);
+    out[2] = estimateSDFError(mtsdf, shape, t, 1, FILL_ODD);
+    return 0;
+}
+
 // Re-entrancy (the reference's generators are free functions without shared state, msdfgen.h:47-69): nThreads host threads
 // generate concurrently, each its own Shape object and its own bitmap of its own size (w+thread, h+thread), `reps` times.
 // out: the threads' [h+t][w+t][3] images back to back.  Returns the number of generator calls made.

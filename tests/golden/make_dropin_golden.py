@@ -18,7 +18,7 @@ arrays = {"seeds": seeds}
 for i, seed in enumerate(seeds):
     r = test_dropin._run(lib, synth_glyph(int(seed), cubic_fraction=0.2))
     arrays[f"edges{i}"] = np.int64(r["edges"])
-    for key in ("msdf", "modes", "ec", "stencil", "scanline", "render"):
+    for key in ("msdf", "modes", "ec", "stencil", "scanline", "render", "sdferr"):
         arrays[f"{key}{i}"] = r[key]
 # caller_threads: four threads, sizes (24+t) x (20+t), colouring seed t — the reference's images for the re-entrancy test
 for t, img in enumerate(test_dropin._threads(lib, synth_glyph(321, cubic_fraction=0.2), 4, 1)):

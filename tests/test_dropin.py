@@ -64,6 +64,9 @@ def _run(lib, g, w=24, h=20):
     e = np.full(4 * h * w * 3 + h * w, np.nan, np.float32)
     assert lib.caller_render(*_args(g), C.c_int(w), C.c_int(h), e.ctypes.data_as(C.POINTER(C.c_float))) == 0
     res["render"] = e
+    f = np.full(3, np.nan, np.float64)
+    assert lib.caller_estimate(*_args(g), C.c_int(w), C.c_int(h), f.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    res["sdferr"] = f
     return res
 
 
@@ -96,6 +99,7 @@ def test_b200_build_matches_reference_build():
             assert over == 0 and max_abs <= 1e-4, (key, seed, bits, max_abs)
             assert np.array_equal(to_bytes(mine[key]), to_bytes(want))
         assert np.array_equal(mine["stencil"], z[f"stencil{i}"])
+        assert np.array_equal(mine["sdferr"], z[f"sdferr{i}"]), (mine["sdferr"], z[f"sdferr{i}"])
 
 
 def _threads(lib, g, n_threads, reps, w=24, h=20):
