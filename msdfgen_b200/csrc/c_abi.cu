@@ -114,6 +114,7 @@ struct b200msdf_batch {
     float *outOverride = nullptr;   // final texels go here instead of `out` (device-accessible pinned host memory of the caller)
     bool ecRan = false;
     float *current = nullptr;       // device pointer to the most recent result (raw field after k1, final output after a full launch)
+    DevBuf bigFrecs, bigExtent;
     DevBuf points, orders, colors, cbegin, windings, glyphs, tiles, bigGlyphs, bigRecs, bigCull, bigPerp, field, out, stencil, candidates, candCount;
     DevBuf signMatch;             // scanline pass of multi-channel fields: per-texel match flags (never the EC stencil)
     DevBuf bytes, byteTargets;    // 8-bit output path
@@ -132,7 +133,7 @@ struct b200msdf_batch {
     std::vector<int> hBig;
     void release() {
         points.release(); orders.release(); colors.release(); cbegin.release(); windings.release(); glyphs.release(); tiles.release();
-        bigGlyphs.release(); bigRecs.release(); bigCull.release(); bigPerp.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); scratchW.release(); bytes.release(); byteTargets.release(); signMatch.release();
+        bigGlyphs.release(); bigRecs.release(); bigCull.release(); bigPerp.release(); bigFrecs.release(); bigExtent.release(); field.release(); out.release(); stencil.release(); candidates.release(); candCount.release(); counters.release(); scratch.release(); scratchW.release(); bytes.release(); byteTargets.release(); signMatch.release();
         blocks.release(); blockWork.release(); filt.release(); tileFilt.release(); k1Counters.release(); recheck.release();
     }
 };
@@ -145,7 +146,7 @@ struct b200msdf_ctx {
     PinBuf pinOut, pinIn, pinDesc;  // pinDesc: staging of per-batch descriptors (glyphs, tiles) so that their H2D copies are true async DMAs
     cudaEvent_t descDone = nullptr; // the last copy out of pinDesc
     uint64_t launches = 0;
-    unsigned k1Parts = 3;           // per-kernel timing (b200msdf_batch_launch_stages): bit 0 k1a_filter, bit 1 k1b_exact + recheck
+    unsigned k1Parts = 3;           // per-kernel timing (b200msdf_batch_launch_stages): bit 0 k1a_filter, bit 1 k1b_exact
     // resident CTAs per SM of every kernel launched through this context, and the dynamic-shared-memory opt-in that goes with
     // it: both are per DEVICE, and a context is bound to one device
     std::unordered_map<const void *, int> occupancy;
@@ -251,6 +252,7 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
         unsigned nSeg = d.s1-d.s0;
         if (nSeg > SMEM_RECORDS) {
             d.recBase = (int) bigRecs;
+            d.bigIndex = (int) b->hBig.size();
             bigRecs += nSeg;
             b->hBig.push_back(g);
             if ((int) nSeg > b->maxBigSegs) b->maxBigSegs = (int) nSeg;
@@ -265,8 +267,10 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
                     b->hBlocks.push_back(td);
                 }
             }
-        } else
+        } else {
             d.recBase = -1;
+            d.bigIndex = -1;
+        }
         for (size_t p0 = 0; p0 < px; p0 += TILE_PIXELS) {
             TileDesc td;
             td.glyph = (unsigned) g;
@@ -370,6 +374,8 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
         if ((rc = b->bigRecs.reserve(sizeof(SegRec)*bigRecs))) return rc;
         if ((rc = b->bigCull.reserve(sizeof(CullRec)*bigRecs))) return rc;
         if ((rc = b->bigPerp.reserve(sizeof(PerpRec)*bigRecs))) return rc;
+        if ((rc = b->bigFrecs.reserve(sizeof(FRec)*bigRecs))) return rc;
+        if ((rc = b->bigExtent.reserve(sizeof(unsigned)*b->hBig.size()))) return rc;
         CUDA_TRY(cudaMemcpyAsync(b->bigGlyphs.p, b->hBig.data(), sizeof(int)*b->hBig.size(), cudaMemcpyHostToDevice, st));
         if ((rc = b->blocks.reserve(sizeof(TileDesc)*(b->hBlocks.size()+1)))) return rc;
         if (!b->hBlocks.empty())
@@ -427,6 +433,13 @@ int grid_for(b200msdf_ctx *ctx, K kernel, int nTiles, size_t dynSmem, int thread
     else {
         if (dynSmem)
             CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) dynSmem));
+        // One shared-memory carve-out for every kernel of the pipeline: consecutive kernels with different carve-outs make the SMs
+        // drain and reconfigure their L1/shared split at every kernel boundary (B200MSDF_CARVEOUT=percent, -1 = driver's choice)
+        {
+            static const int carveout = getenv("B200MSDF_CARVEOUT") ? atoi(getenv("B200MSDF_CARVEOUT")) : -1;
+            if (carveout >= 0)
+                CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carveout));
+        }
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, threads, dynSmem));
         cache[(const void *) kernel] = perSM;
     }
@@ -486,6 +499,7 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
         if ((rc = bb->filt.reserve(roundWords*sizeof(unsigned)+256))) return rc;
         if ((rc = bb->k1Counters.reserve(sizeof(int)*(2*(size_t) rounds+1)))) return rc;
         CUDA_TRY(cudaMemsetAsync(bb->k1Counters.p, 0, sizeof(int)*(2*(size_t) rounds+1), ctx->stream));
+#if B200_GUARD_MODE == 2
         // guard band of the fast foot-point roots: k1b flags the texels (and tiles) whose outcome hinged on the last bits of a root
         const size_t maskBytes = ((bb->texels+31)/32)*4, tileBytes = ((size_t) P.nSmallTiles+3)&~size_t(3);
         if ((rc = bb->recheck.reserve(maskBytes+tileBytes+16))) return rc;
@@ -493,6 +507,7 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
         P.recheckMask = bb->recheck.as<unsigned>();
         P.recheckTiles = bb->recheck.as<unsigned char>()+maskBytes;
         P.recheckAny = reinterpret_cast<int *>(bb->recheck.as<unsigned char>()+maskBytes+tileBytes);
+#endif
         int *const batchCounters = P.counters;
         P.counters = bb->k1Counters.as<int>();
         for (int r = 0; r < rounds && !rc; ++r) {
@@ -505,9 +520,11 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
             P.counterIndex = 2*r+1;
             if (!rc && (ctx->k1Parts&2u)) rc = launch_tiles(ctx, k1b_exact<MODE, OVERLAP>, P, scratch, 0, K1_THREADS);
         }
+#if B200_GUARD_MODE == 2
         // ... and the flagged texels are recomputed with the literal solver (a handful per atlas; tiles without any are skipped)
         P.tileBegin = 0; P.tileEnd = P.nSmallTiles; P.counterIndex = 2*rounds;
         if (!rc && (ctx->k1Parts&2u)) rc = launch_tiles(ctx, k1_distance_field<MODE, OVERLAP, true>, P, scratch);
+#endif
         P.counters = batchCounters;
         P.tileBegin = 0; P.tileEnd = P.nSmallTiles; P.counterIndex = 0;
         if (rc) return rc;
@@ -616,6 +633,8 @@ void fill_params(b200msdf_ctx *ctx, b200msdf_batch *b, const b200msdf_config *cf
     P.bigRecs = b->bigRecs.as<SegRec>();
     P.bigCull = b->bigCull.as<CullRec>();
     P.bigPerp = b->bigPerp.as<PerpRec>();
+    P.bigFrecs = b->bigFrecs.as<FRec>();
+    P.bigExtent = b->bigExtent.as<unsigned>();
     P.counters = b->counters.as<int>();
     ctx->cur = b;
     P.ecMode = cfg->ec_mode;
@@ -633,9 +652,14 @@ int launch_prologue(b200msdf_ctx *ctx, b200msdf_batch *b, KernelParams &P) {
     ++ctx->launches;
     if (b->nBig) {
         dim3 grid(64, (unsigned) (b->nBig < 1024 ? b->nBig : 1024));
-        k0_prepare_big<<<grid, 128, 0, ctx->stream>>>(P.raw, P.glyphs, b->bigGlyphs.as<int>(), b->nBig, b->bigRecs.as<SegRec>(), b->bigCull.as<CullRec>(), b->bigPerp.as<PerpRec>());
+        CUDA_TRY(cudaMemsetAsync(b->bigExtent.p, 0, sizeof(unsigned)*(size_t) b->nBig, ctx->stream));
+        k0_prepare_big<<<grid, 128, 0, ctx->stream>>>(P.raw, P.glyphs, b->bigGlyphs.as<int>(), b->nBig, b->bigRecs.as<SegRec>(), b->bigCull.as<CullRec>(), b->bigPerp.as<PerpRec>(),
+                                                      b->bigExtent.as<unsigned>());
         CUDA_TRY(cudaGetLastError());
-        ++ctx->launches;
+        k0_prepare_big_filter<<<grid, 128, 0, ctx->stream>>>(P.glyphs, b->bigGlyphs.as<int>(), b->nBig, b->bigRecs.as<SegRec>(), b->bigFrecs.as<FRec>(),
+                                                             b->bigExtent.as<unsigned>(), b->mode <= 2 ? 1 : 0);
+        CUDA_TRY(cudaGetLastError());
+        ctx->launches += 2;
     }
     return 0;
 }

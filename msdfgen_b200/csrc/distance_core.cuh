@@ -121,6 +121,7 @@ struct GlyphDesc {
     int nonEmptyContours;
     int x0, y0;                     // pixel origin of the block inside the full image (regions; 0 otherwise)
     int recBase;                    // >= 0: prepared records live in the global big-shape buffer at this index; -1: staged in smem
+    int bigIndex;                   // index among the batch's big shapes (recBase >= 0)
 };
 
 struct RawShapes {
@@ -507,7 +508,11 @@ __device__ __forceinline__ SDist sd_linear(const SegRec &s, d2 p, double need) {
 // the root: a root within 1e-9 of the ends of (0,1), or a distance within 1e-13 (relative) of the running minimum — the fast
 // path's polished roots are accurate to ~1e-14 but not bit-faithful, so such an edge is re-evaluated with the literal solver.
 #ifndef B200_GUARD_BAND
+#ifdef B200_GUARD_MODE
+#define B200_GUARD_BAND (B200_GUARD_MODE != 0)
+#else
 #define B200_GUARD_BAND 1
+#endif
 #endif
 __device__ __forceinline__ void quad_root(d2 qa, d2 ab, d2 br, double t, double &minDistance, bool &interior, bool &unsure) {
 #if B200_GUARD_BAND
@@ -573,8 +578,8 @@ __device__ __forceinline__ unsigned char &guard_flag() {
 }
 
 // LITERAL = false: fast foot-point roots (fp32 closed form + fp64 polish); guard_flag() is raised when the guard band of
-// quad_root was hit — the caller then has the texel re-evaluated with LITERAL = true (k1b_exact -> k1_distance_field recheck
-// launch), which takes the reference's closed form with correctly rounded acos / cos / pow for every quadratic segment.
+// quad_root was hit — k1b_exact then re-evaluates the texel with LITERAL = true (texel_literal, kernels.cuh), which takes the
+// reference's closed form with correctly rounded acos / cos / pow for every quadratic segment.
 template <bool LITERAL>
 __device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need) {
     d2 qa = s.p0-p;
@@ -1162,6 +1167,64 @@ __device__ __noinline__ double near_edge_dd(double cd, int near, const SegRec *r
     return dd;
 }
 
+// Second half of OverlappingContourCombiner::distance (contour-combiners.cpp:94-134) over the folded selectors and the parked
+// contour distances.
+template <int MODE>
+__device__ __forceinline__ void fold_finish(const FoldAcc<MODE> &shape, const FoldAcc<MODE> &inner, const FoldAcc<MODE> &outer, FoldStore st, int nc,
+                                            double *out) {
+    const int NOUT = ModeTraits<MODE>::NOUT;
+    double shapeD[NOUT], innerD[NOUT], outerD[NOUT], dist[NOUT];
+    fold_distance<MODE>(shape, shapeD);
+    fold_distance<MODE>(inner, innerD);
+    fold_distance<MODE>(outer, outerD);
+    const double innerScalar = resolve<MODE>(innerD), outerScalar = resolve<MODE>(outerD);
+    int winding;
+    if (innerScalar >= 0 && fabs(innerScalar) <= fabs(outerScalar)) {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) dist[k] = innerD[k];
+        winding = 1;
+    } else if (outerScalar <= 0 && fabs(outerScalar) < fabs(innerScalar)) {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) dist[k] = outerD[k];
+        winding = -1;
+    } else {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) out[k] = shapeD[k];
+        return;
+    }
+    // Pass 0: same-winding contours refine the inner/outer pick.  Pass 1: the others may override it.
+    for (int pass = 0; pass < 2; ++pass)
+        for (int c = 0; c < nc; ++c) {
+            const int w = st.w(c);
+            // (the winding test first: it spares the loads of the distances of half the contours)
+            if (pass == 0 ? w != winding : w == winding)
+                continue;
+            double cd[NOUT];
+            #pragma unroll
+            for (int k = 0; k < NOUT; ++k)
+                cd[k] = st.cd(c, k);
+            const double rc = resolve<MODE>(cd), rdist = resolve<MODE>(dist);
+            bool take;
+            if (pass == 0) {
+                if (winding > 0)
+                    take = fabs(rc) < fabs(outerScalar) && rc > rdist;
+                else
+                    take = fabs(rc) < fabs(innerScalar) && rc < rdist;
+            } else
+                take = rc*rdist >= 0 && fabs(rc) < fabs(rdist);
+            if (take) {
+                #pragma unroll
+                for (int k = 0; k < NOUT; ++k) dist[k] = cd[k];
+            }
+        }
+    if (resolve<MODE>(dist) == resolve<MODE>(shapeD)) {
+        #pragma unroll
+        for (int k = 0; k < NOUT; ++k) dist[k] = shapeD[k];
+    }
+    #pragma unroll
+    for (int k = 0; k < NOUT; ++k) out[k] = dist[k];
+}
+
 template <int MODE, typename IT>
 __device__ __forceinline__ void shape_distance_fold(const SegRec *recs, int nRec, IT it, d2 p, FoldStore st, double *out) {
     const int NCH = ModeTraits<MODE>::NCH;
@@ -1215,56 +1278,7 @@ __device__ __forceinline__ void shape_distance_fold(const SegRec *recs, int nRec
             j0 = j1+1;
         }
     }
-    double shapeD[NOUT], innerD[NOUT], outerD[NOUT], dist[NOUT];
-    fold_distance<MODE>(shape, shapeD);
-    fold_distance<MODE>(inner, innerD);
-    fold_distance<MODE>(outer, outerD);
-    const double innerScalar = resolve<MODE>(innerD), outerScalar = resolve<MODE>(outerD);
-    int winding;
-    if (innerScalar >= 0 && fabs(innerScalar) <= fabs(outerScalar)) {
-        #pragma unroll
-        for (int k = 0; k < NOUT; ++k) dist[k] = innerD[k];
-        winding = 1;
-    } else if (outerScalar <= 0 && fabs(outerScalar) < fabs(innerScalar)) {
-        #pragma unroll
-        for (int k = 0; k < NOUT; ++k) dist[k] = outerD[k];
-        winding = -1;
-    } else {
-        #pragma unroll
-        for (int k = 0; k < NOUT; ++k) out[k] = shapeD[k];
-        return;
-    }
-    // Pass 0: same-winding contours refine the inner/outer pick.  Pass 1: the others may override it.
-    for (int pass = 0; pass < 2; ++pass)
-        for (int c = 0; c < nc; ++c) {
-            const int w = st.w(c);
-            // (the winding test first: it spares the loads of the distances of half the contours)
-            if (pass == 0 ? w != winding : w == winding)
-                continue;
-            double cd[NOUT];
-            #pragma unroll
-            for (int k = 0; k < NOUT; ++k)
-                cd[k] = st.cd(c, k);
-            const double rc = resolve<MODE>(cd), rdist = resolve<MODE>(dist);
-            bool take;
-            if (pass == 0) {
-                if (winding > 0)
-                    take = fabs(rc) < fabs(outerScalar) && rc > rdist;
-                else
-                    take = fabs(rc) < fabs(innerScalar) && rc < rdist;
-            } else
-                take = rc*rdist >= 0 && fabs(rc) < fabs(rdist);
-            if (take) {
-                #pragma unroll
-                for (int k = 0; k < NOUT; ++k) dist[k] = cd[k];
-            }
-        }
-    if (resolve<MODE>(dist) == resolve<MODE>(shapeD)) {
-        #pragma unroll
-        for (int k = 0; k < NOUT; ++k) dist[k] = shapeD[k];
-    }
-    #pragma unroll
-    for (int k = 0; k < NOUT; ++k) out[k] = dist[k];
+    fold_finish<MODE>(shape, inner, outer, st, nc, out);
 }
 
 template <int MODE, bool OVERLAP, bool LITERAL = false>

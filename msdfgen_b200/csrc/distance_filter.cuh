@@ -535,4 +535,173 @@ __device__ __forceinline__ void exact_texel(const SegRec *recs, int nRec, const 
         combine_parked<MODE>(store, nc, out);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Big shapes (k1_big_blocks): the same filter in front of the per-texel walk over a warp's record sub-list.  One kernel, no mask
+// words: pass 1 gives U[k] over the contour's listed records, pass 2 evaluates a survivor — or a dropped edge's perpendicular
+// candidate — exactly on the spot (records of big shapes live in global memory; their FRecs are 64 bytes instead of 352).
+// OVERLAP: contours are folded into the shape / inner / outer accumulators as they finish (shape_distance_fold).
+template <int MODE, bool OVERLAP, typename IT>
+__device__ __forceinline__ void shape_distance_list_filtered(const SegRec *recs, const FRec *frecs, int nRec, IT it, d2 O, float slack, d2 p,
+                                                             FoldStore st, double *out) {
+    const int NCH = ModeTraits<MODE>::NCH;
+    const int NOUT = ModeTraits<MODE>::NOUT;
+    const float plx = float(p.x-O.x), ply = float(p.y-O.y);
+    FoldAcc<MODE> shape, inner, outer;
+    if (OVERLAP) { fold_init(shape); fold_init(inner); fold_init(outer); }
+    int nc = 0;
+    Sel<MODE> cur;
+    sel_init(cur);
+    int j0 = 0;
+    while (j0 < nRec) {
+        const int j1 = OVERLAP ? it.group_last(recs, j0, nRec) : nRec-1;
+        // ---- pass 1
+        float U[NCH];
+        #pragma unroll
+        for (int k = 0; k < NCH; ++k)
+            U[k] = 3.0e38f;
+        for (int i = j0; i <= j1; ++i) {
+            const int j = it.at(i);
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(frecs+j));
+            const float4 m = __ldg(reinterpret_cast<const float4 *>(frecs+j)+3);
+            const int mask = __float_as_int(m.z);
+            const float apx = plx-c.x, apy = ply-c.y;
+            float t = __saturatef(__fmaf_rn(apx, c.z, apy*c.w)*m.x);
+            if (mask&FREC_CUBIC)
+                t = t >= .5f ? 1.f : 0.f;
+            const float qx = __fmaf_rn(-t, c.z, apx), qy = __fmaf_rn(-t, c.w, apy);
+            const float u = __fmaf_rn(sqrt_approx(__fmaf_rn(qx, qx, qy*qy)), 1.000004f, m.y);
+            #pragma unroll
+            for (int k = 0; k < NCH; ++k)
+                if (mask&(1<<k))
+                    U[k] = fminf(U[k], u);
+        }
+        // ---- pass 2 with the exact work in place
+        for (int i = j0; i <= j1; ++i) {
+            const int j = it.at(i);
+            const float4 c = __ldg(reinterpret_cast<const float4 *>(frecs+j));
+            const float4 m = __ldg(reinterpret_cast<const float4 *>(frecs+j)+3);
+            const int fmask = __float_as_int(m.z);
+            float Um = 0.f;
+            #pragma unroll
+            for (int k = 0; k < NCH; ++k)
+                if (fmask&(1<<k))
+                    Um = fmaxf(Um, U[k]);
+            const float apx = plx-c.x, apy = ply-c.y;
+            const float t = __saturatef(__fmaf_rn(apx, c.z, apy*c.w)*m.x);
+            const float qx = __fmaf_rn(-t, c.z, apx), qy = __fmaf_rn(-t, c.w, apy);
+            const float d2f = __fmaf_rn(qx, qx, qy*qy);
+            const float thr = Um+m.y;
+            if (!(d2f > thr*thr*1.00001f)) {
+                // survivor: exactly as the reference (edge-selectors.cpp:129-160 / 174-227)
+                const SegRec &s = recs[j];
+                const int mask = (MODE == 1 || MODE == 2) ? 1 : s.color;
+                double need = 0;
+                #pragma unroll
+                for (int k = 0; k < NCH; ++k)
+                    if (mask&(1<<k))
+                        need = dmax(need, dmin(fabs(cur.ch[k].d), double(U[k])*1.000001));
+                const SDist r = signed_distance(s, p, need);
+                if (fabs(r.d) <= need) {
+                    const int near = (j<<2)|r.side;
+                    #pragma unroll
+                    for (int k = 0; k < NCH; ++k)
+                        if (mask&(1<<k))
+                            if (sd_less(r.d, r.dot, cur.ch[k].d, cur.ch[k].dot)) {
+                                cur.ch[k].d = r.d; cur.ch[k].dot = r.dot; cur.ch[k].near = near;
+                            }
+                }
+                if (MODE != 1) {
+                    const d2 ap = p-s.p0;
+                    const double pdA = cross(ap, s.aDir);
+                    if (dot(ap, s.aBis) > 0 && -dot(ap, s.aDir) > 0 && fabs(pdA) < fabs(r.d)) {
+                        #pragma unroll
+                        for (int k = 0; k < NCH; ++k)
+                            if (mask&(1<<k))
+                                chan_add_perp(cur.ch[k], pdA);
+                    }
+                    const d2 bp = p-s.pEnd;
+                    const double pdB = cross(bp, s.bDir);
+                    if (-dot(bp, s.bBis) > 0 && dot(bp, s.bDir) > 0 && fabs(pdB) < fabs(r.d)) {
+                        #pragma unroll
+                        for (int k = 0; k < NCH; ++k)
+                            if (mask&(1<<k))
+                                chan_add_perp(cur.ch[k], pdB);
+                    }
+                }
+            } else if (MODE != 1) {
+                // dropped edge: its perpendicular candidates (see the header of this file)
+                const float4 dir = __ldg(reinterpret_cast<const float4 *>(frecs+j)+1);
+                const float4 bis = __ldg(reinterpret_cast<const float4 *>(frecs+j)+2);
+                const float lim = Um+slack;
+                const float pdAf = __fmaf_rn(apx, dir.y, -apy*dir.x);
+                const bool cA = !(fabsf(pdAf) > lim) && !(__fmaf_rn(apx, bis.x, apy*bis.y) < -slack) && !(__fmaf_rn(apx, dir.x, apy*dir.y) > slack);
+                const float bpx = apx-c.z, bpy = apy-c.w;
+                const float pdBf = __fmaf_rn(bpx, dir.w, -bpy*dir.z);
+                const bool cB = !(fabsf(pdBf) > lim) && !(__fmaf_rn(bpx, bis.z, bpy*bis.w) > slack) && !(__fmaf_rn(bpx, dir.z, bpy*dir.w) < -slack);
+                if (cA || cB) {
+                    const SegRec &s = recs[j];
+                    const int mask = MODE == 2 ? 1 : s.color;
+                    const double UmD = double(Um);
+                    if (cA) {
+                        const d2 ap = p-s.p0;
+                        const double pdA = cross(ap, s.aDir);
+                        if (dot(ap, s.aBis) > 0 && -dot(ap, s.aDir) > 0 && fabs(pdA) <= UmD) {
+                            #pragma unroll
+                            for (int k = 0; k < NCH; ++k)
+                                if (mask&(1<<k))
+                                    chan_add_perp(cur.ch[k], pdA);
+                        }
+                    }
+                    if (cB) {
+                        const d2 bp = p-s.pEnd;
+                        const double pdB = cross(bp, s.bDir);
+                        if (-dot(bp, s.bBis) > 0 && dot(bp, s.bDir) > 0 && fabs(pdB) <= UmD) {
+                            #pragma unroll
+                            for (int k = 0; k < NCH; ++k)
+                                if (mask&(1<<k))
+                                    chan_add_perp(cur.ch[k], pdB);
+                        }
+                    }
+                }
+            }
+        }
+        if (OVERLAP) {
+            // the contour's own distances, its merges, and what the second half of the combiner reads back (shape_distance_fold)
+            double dd[NCH], cd[NOUT];
+            double td = cur.ch[0].d, tdot = cur.ch[0].dot;
+            #pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+                cd[k] = cur.ch[k].d;
+                dd[k] = DBL_MAX;
+                if (MODE != 1) {
+                    dd[k] = near_edge_dd(cur.ch[k].d, cur.ch[k].near, recs, p.x, p.y);
+                    const double mm = cur.ch[k].d < 0 ? cur.ch[k].neg : cur.ch[k].pos;
+                    cd[k] = fabs(dd[k]) < fabs(mm) ? dd[k] : mm;
+                }
+                if (MODE == 4 && k > 0 && sd_less(cur.ch[k].d, cur.ch[k].dot, td, tdot)) { td = cur.ch[k].d; tdot = cur.ch[k].dot; }
+            }
+            if (MODE == 4)
+                cd[3] = td;
+            const int w = recs[it.at(j1)].winding;
+            const double rd = resolve<MODE>(cd);
+            fold_merge<MODE>(shape, cur, dd);
+            if (w > 0 && rd >= 0)
+                fold_merge<MODE>(inner, cur, dd);
+            if (w < 0 && rd <= 0)
+                fold_merge<MODE>(outer, cur, dd);
+            #pragma unroll
+            for (int k = 0; k < NOUT; ++k)
+                st.cd(nc, k) = cd[k];
+            st.w(nc) = (signed char) w;
+            sel_init(cur);
+            ++nc;
+        }
+        j0 = j1+1;
+    }
+    if (!OVERLAP)
+        sel_distance<MODE>(cur, recs, p, out);
+    else
+        fold_finish<MODE>(shape, inner, outer, st, nc, out);
+}
+
 }  // namespace b200

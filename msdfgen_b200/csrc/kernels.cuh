@@ -42,6 +42,8 @@ struct KernelParams {
     const SegRec *bigRecs;        // prepared records of big shapes
     const CullRec *bigCull;       // same indexing as bigRecs
     const PerpRec *bigPerp;
+    const FRec *bigFrecs;         // fp32 filter records of big shapes (same indexing as bigRecs)
+    unsigned *bigExtent;          // per big glyph: float bits of the largest |local coordinate| of its control points
     int *counters;                // tile counters: [0],[3] k1 small/big, [1] k2, [2],[4] k3 small/big
     struct Candidate *candidates; // k2 -> k3: per-tile slots of exact-distance checks, candCap per tile
     int *candCount;               // per-tile number of pushes (may exceed candCap: overflow texels carry EC_FLAG_RECHECK)
@@ -58,7 +60,7 @@ struct KernelParams {
     double *scratch;              // per-thread contour-distance slices for many-contour shapes
     signed char *scratchW;        // k1_big_blocks: per-thread winding slices (same indexing)
     size_t scratchStride;         // = gridDim.x * CTA_THREADS
-    unsigned *recheckMask;        // k1b -> recheck launch: one bit per texel of the batch (guard band of the fast root path)
+    unsigned *recheckMask;        // B200_GUARD_MODE 2: k1b -> recheck launch, one bit per texel of the batch
     unsigned char *recheckTiles;  // one byte per small tile: the tile has such texels
     int *recheckAny;              // any texel flagged at all (the recheck launch returns at once otherwise)
     unsigned *filt;               // k1a -> k1b: per-unit filter words (distance_filter.cuh)
@@ -70,6 +72,11 @@ struct KernelParams {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
+
+// origin of the filter's local coordinates: the centre of the glyph's texel block in shape units
+__device__ __forceinline__ d2 filter_origin(const GlyphDesc &g) {
+    return mk((g.x0+.5*g.w)/g.sx-g.tx, (g.y0+.5*g.h)/g.sy-g.ty);
+}
 
 __global__ void k0_windings(RawShapes raw, int nContours, int8_t *windings, int *counters) {
     int c = blockIdx.x*blockDim.x+threadIdx.x;
@@ -83,19 +90,48 @@ __global__ void k0_windings(RawShapes raw, int nContours, int8_t *windings, int 
 }
 
 // items: (glyph index, evaluation position) pairs are implied by a prefix table: bigGlyphs[i] = glyph index, bigBase[i] = first record
-__global__ void k0_prepare_big(RawShapes raw, const GlyphDesc *glyphs, const int *bigGlyphs, int nBig, SegRec *recs, CullRec *cull, PerpRec *perp) {
+__global__ void k0_prepare_big(RawShapes raw, const GlyphDesc *glyphs, const int *bigGlyphs, int nBig, SegRec *recs, CullRec *cull, PerpRec *perp,
+                               unsigned *extent) {
     for (int i = blockIdx.y; i < nBig; i += gridDim.y) {
         GlyphDesc g = glyphs[bigGlyphs[i]];
         unsigned n = g.s1-g.s0;
+        const d2 O = filter_origin(g);
         for (unsigned j = blockIdx.x*blockDim.x+threadIdx.x; j < n; j += gridDim.x*blockDim.x) {
             SegRec &r = recs[size_t(g.recBase)+j];
             prepare_record(raw, g, j, r);
+            atomicMax(&extent[i], __float_as_uint(record_extent(r, O)));
             CullRec c;
             c.bc = r.bc; c.br = r.br; c.color = r.color; c.contour = r.contour; c.p0 = r.p0;
             cull[size_t(g.recBase)+j] = c;
             PerpRec q;
             q.pEnd = r.pEnd; q.aDir = r.aDir; q.bDir = r.bDir; q.aBis = r.aBis; q.bBis = r.bBis;
             perp[size_t(g.recBase)+j] = q;
+        }
+    }
+}
+
+// slack of the fp32 filter for glyph g given the extent of its control points (distance_filter.cuh)
+__device__ __forceinline__ float filter_slack(const GlyphDesc &g, d2 O, float extent) {
+    float M = extent;
+    M = fmaxf(M, float_up((.5*g.w+1)/fabs(g.sx)));
+    M = fmaxf(M, float_up((.5*g.h+1)/fabs(g.sy)));
+    return M*1.52587890625e-5f+float_up(fmax(fabs(O.x), fabs(O.y)))*5.7e-14f+1e-37f;       // 2^-16 M + 2^-44 |O|
+}
+
+// second preparation pass of big shapes: the filter records (need the shape's extent, known after k0_prepare_big)
+__global__ void k0_prepare_big_filter(const GlyphDesc *glyphs, const int *bigGlyphs, int nBig, const SegRec *recs, FRec *frecs, const unsigned *extent,
+                                      int singleChannel) {
+    for (int i = blockIdx.y; i < nBig; i += gridDim.y) {
+        GlyphDesc g = glyphs[bigGlyphs[i]];
+        unsigned n = g.s1-g.s0;
+        const d2 O = filter_origin(g);
+        const float slack = filter_slack(g, O, __uint_as_float(extent[i]));
+        for (unsigned j = blockIdx.x*blockDim.x+threadIdx.x; j < n; j += gridDim.x*blockDim.x) {
+            FRec f;
+            make_filter_record<3>(recs[size_t(g.recBase)+j], O, slack, f);
+            if (singleChannel)
+                f.mask = (f.mask&~7)|1;
+            frecs[size_t(g.recBase)+j] = f;
         }
     }
 }
@@ -165,9 +201,9 @@ __device__ __forceinline__ void store_tile(float *dst, const float *staged, int 
 }
 
 // The full walk (every texel evaluates every record with the exact fp64 culling of sel_add_edge): the distance kernel of
-// round 1, kept for two jobs.  RECHECK = false: A/B baseline (B200MSDF_K1_LEGACY=1).  RECHECK = true: launched after k1b_exact
-// over the tiles it flagged, it recomputes — with the LITERAL root solver for every quadratic segment — exactly the texels
-// whose fast-path result hinged on the last bits of a root (guard band), and overwrites them.
+// round 1, kept for two jobs.  RECHECK = false: A/B baseline (B200MSDF_K1_LEGACY=1).  RECHECK = true (B200_GUARD_MODE 2): launched
+// after k1b_exact, it recomputes — with the LITERAL root solver for every quadratic segment — exactly the texels k1b flagged
+// (guard band of the fast root path) and overwrites them; it returns at once when nothing was flagged.
 template <int MODE, bool OVERLAP, bool RECHECK>
 __global__ void __launch_bounds__(CTA_THREADS, 2) k1_distance_field(KernelParams P) {
     const bool BIG = false;
@@ -324,11 +360,6 @@ __device__ __forceinline__ d2 texel_point(const GlyphDesc &g, int x, int yOut) {
     return mk(ddiv(g.x0+x+.5, g.sx)-g.tx, ddiv(g.y0+y+.5, g.sy)-g.ty);
 }
 
-// origin of the filter's local coordinates: the centre of the glyph's texel block in shape units
-__device__ __forceinline__ d2 filter_origin(const GlyphDesc &g) {
-    return mk((g.x0+.5*g.w)/g.sx-g.tx, (g.y0+.5*g.h)/g.sy-g.ty);
-}
-
 // group ends (positions after the last record of every non-empty contour) and filter words per texel; one thread
 template <int MODE, bool OVERLAP>
 __device__ __forceinline__ void build_groups(const KernelParams &P, const GlyphDesc &g, int *groupEnd, int *nGroups, unsigned *wordsPerTexel) {
@@ -435,6 +466,24 @@ __global__ void __launch_bounds__(K1_THREADS, 8) k1a_filter(KernelParams P) {
     }
 }
 
+// How texels whose fast-path roots hit the guard band (distance_core.cuh: quad_root) get their literal re-evaluation:
+//   0  no guard band;  1  in k1b_exact, by an out-of-line call per flagged texel;  2  by a second launch of the full-walk kernel over
+//   the flagged texels (k1b only records them).  Measured on B200 (headline atlas, k1a+k1b): see profiles/README.md.
+#ifndef B200_GUARD_MODE
+#define B200_GUARD_MODE 2
+#endif
+
+// ShapeDistanceFinder::oneShotDistance by the full walk with LITERAL roots (distance_core.cuh), mapped and stored as floats.
+template <int MODE, bool OVERLAP>
+__device__ __noinline__ void texel_literal(const SegRec *recs, int nRec, double px, double py, ContourStore store, double dmScale, double dmTranslate,
+                                           float *out) {
+    double dist[ModeTraits<MODE>::NOUT];
+    shape_distance<MODE, OVERLAP, true>(recs, nRec, mk(px, py), store, dist);
+    #pragma unroll
+    for (int k = 0; k < ModeTraits<MODE>::NOUT; ++k)
+        out[k] = float(dmScale*(dist[k]+dmTranslate));
+}
+
 #ifndef K1B_MIN_CTAS
 #define K1B_MIN_CTAS 4
 #endif
@@ -504,21 +553,31 @@ __global__ void __launch_bounds__(K1_THREADS, K1B_MIN_CTAS) k1b_exact(KernelPara
             const d2 p = texel_point(s_g, x, yOut);
             double dist[NOUT];
             exact_texel<MODE, OVERLAP>(s_recs, nRec, s_groupEnd, s_nGroups, tileWords+size_t(u)*words*32u+lane, p, store, dist);
-            const bool unsure = guard_flag() != 0;
-            if (unsure)
-                guard_flag() = 0;
-            if (unsure && valid) {
-                // guard band hit: the recheck launch (k1_distance_field<.., LITERAL>) recomputes this texel with the literal solver
-                const size_t t = size_t(s_g.texelOffset)+size_t(yOut)*w+x;
-                atomicOr(&P.recheckMask[t>>5], 1u<<(t&31));
-                P.recheckTiles[tile] = 1;
-                *P.recheckAny = 1;
-            }
             if (valid) {
                 #pragma unroll
                 for (int k = 0; k < NOUT; ++k)
                     s_out[warp][lane*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));      // DistanceMapping::operator()
             }
+#if B200_GUARD_MODE == 1
+            if (guard_flag()) {
+                // guard band of the fast foot-point roots hit (a handful of texels per atlas): the texel is recomputed by the full
+                // walk with the literal, correctly rounded root solver for every quadratic segment — out of line, cold
+                guard_flag() = 0;
+                if (valid)
+                    texel_literal<MODE, OVERLAP>(s_recs, nRec, p.x, p.y, store, s_g.dmScale, s_g.dmTranslate, &s_out[warp][lane*NOUT]);
+            }
+#elif B200_GUARD_MODE == 2
+            if (guard_flag()) {
+                // guard band hit: the recheck launch (k1_distance_field<.., true>) recomputes this texel with the literal solver
+                guard_flag() = 0;
+                if (valid) {
+                    const size_t t = size_t(s_g.texelOffset)+size_t(yOut)*w+x;
+                    atomicOr(&P.recheckMask[t>>5], 1u<<(t&31));
+                    P.recheckTiles[tile] = 1;
+                    *P.recheckAny = 1;
+                }
+            }
+#endif
             __syncwarp();
             if (grid.blocked) {
                 // 4 rows of 8 texels: 2*NOUT float4 per row, rows contiguous in the warp's slice
@@ -624,6 +683,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
         const SegRec *recs = P.bigRecs+s_g.recBase;
         const CullRec *cull = P.bigCull+s_g.recBase;
         const PerpRec *perp = P.bigPerp+s_g.recBase;
+        const FRec *frecs = P.bigFrecs+s_g.recBase;
+        const d2 O = filter_origin(s_g);
+        const float fslack = filter_slack(s_g, O, __uint_as_float(P.bigExtent[s_g.bigIndex]));
         const int nRec = int(s_g.s1-s_g.s0);
         const int w = s_g.w, h = s_g.h;
         const int blocksX = (w+BLOCK_W-1)/BLOCK_W;
@@ -808,10 +870,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k1_big_blocks(KernelParams P) 
                 const int y = s_g.flip ? h-1-yOut : yOut;
                 d2 p = mk((s_g.x0+x+.5)/s_g.sx-s_g.tx, (s_g.y0+y+.5)/s_g.sy-s_g.ty);
                 double dist[NOUT];
-                if (OVERLAP)
-                    shape_distance_fold<MODE>(recs, nWalk, it, p, store, dist);
-                else
-                    shape_distance_over<MODE, false>(recs, nWalk, it, p, ContourStore(), dist);
+                shape_distance_list_filtered<MODE, OVERLAP>(recs, frecs, nWalk, it, O, fslack, p, store, dist);
                 #pragma unroll
                 for (int k = 0; k < NOUT; ++k)
                     s_out[(yl*BLOCK_W+xl)*NOUT+k] = float(s_g.dmScale*(dist[k]+s_g.dmTranslate));
