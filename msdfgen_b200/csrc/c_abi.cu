@@ -203,6 +203,23 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     if (rc) return rc;
     if (!xf || !dims)
         return fail(B200MSDF_ERR_ARG, "null transformation/dims");
+    // the raw shape arrays go first: with pinned caller memory their DMA runs while the host builds the descriptors below
+    cudaStream_t st = ctx->stream;
+    const size_t nSeg = (size_t) s->n_segments, nCon = (size_t) s->n_contours;
+    if ((rc = b->points.reserve(nSeg*64+64))) return rc;
+    if ((rc = b->orders.reserve(nSeg+16))) return rc;
+    if ((rc = b->colors.reserve(nSeg+16))) return rc;
+    if ((rc = b->cbegin.reserve((nCon+1)*4))) return rc;
+    if (nSeg) {
+        CUDA_TRY(cudaMemcpyAsync(b->points.p, s->points, nSeg*64, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->orders.p, s->orders, nSeg, cudaMemcpyHostToDevice, st));
+        if (s->colors)
+            CUDA_TRY(cudaMemcpyAsync(b->colors.p, s->colors, nSeg, cudaMemcpyHostToDevice, st));
+    }
+    if (s->contour_segment_begin)
+        CUDA_TRY(cudaMemcpyAsync(b->cbegin.p, s->contour_segment_begin, (nCon+1)*4, cudaMemcpyHostToDevice, st));
+    else
+        CUDA_TRY(cudaMemsetAsync(b->cbegin.p, 0, 4, st));
     b->mode = mode;
     b->N = channels_of(mode);
     b->nGlyphs = s->n_glyphs;
@@ -351,12 +368,6 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
     b->nBigRecs = bigRecs;
     b->nBlocks = (int) b->hBlocks.size();
 
-    cudaStream_t st = ctx->stream;
-    size_t nSeg = (size_t) s->n_segments, nCon = (size_t) s->n_contours;
-    if ((rc = b->points.reserve(nSeg*64+64))) return rc;
-    if ((rc = b->orders.reserve(nSeg+16))) return rc;
-    if ((rc = b->colors.reserve(nSeg+16))) return rc;
-    if ((rc = b->cbegin.reserve((nCon+1)*4))) return rc;
     if ((rc = b->windings.reserve(nCon+16))) return rc;
     if ((rc = b->glyphs.reserve(sizeof(GlyphDesc)*(b->hGlyphs.size()+1)))) return rc;
     if ((rc = b->tiles.reserve(sizeof(TileDesc)*(b->hTiles.size()+1)))) return rc;
@@ -381,16 +392,6 @@ int upload_batch(b200msdf_ctx *ctx, b200msdf_batch *b, int mode, const b200msdf_
         if (!b->hBlocks.empty())
             CUDA_TRY(cudaMemcpyAsync(b->blocks.p, b->hBlocks.data(), sizeof(TileDesc)*b->hBlocks.size(), cudaMemcpyHostToDevice, st));
     }
-    if (nSeg) {
-        CUDA_TRY(cudaMemcpyAsync(b->points.p, s->points, nSeg*64, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(b->orders.p, s->orders, nSeg, cudaMemcpyHostToDevice, st));
-        if (s->colors)
-            CUDA_TRY(cudaMemcpyAsync(b->colors.p, s->colors, nSeg, cudaMemcpyHostToDevice, st));
-    }
-    if (s->contour_segment_begin)
-        CUDA_TRY(cudaMemcpyAsync(b->cbegin.p, s->contour_segment_begin, (nCon+1)*4, cudaMemcpyHostToDevice, st));
-    else
-        CUDA_TRY(cudaMemsetAsync(b->cbegin.p, 0, 4, st));
     // glyph and tile descriptors go through pinned staging (a cudaMemcpyAsync from a pageable std::vector is staged and
     // synchronous on the host)
     {

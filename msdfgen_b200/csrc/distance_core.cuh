@@ -580,8 +580,16 @@ __device__ __forceinline__ unsigned char &guard_flag() {
 // LITERAL = false: fast foot-point roots (fp32 closed form + fp64 polish); guard_flag() is raised when the guard band of
 // quad_root was hit — k1b_exact then re-evaluates the texel with LITERAL = true (texel_literal, kernels.cuh), which takes the
 // reference's closed form with correctly rounded acos / cos / pow for every quadratic segment.
+#ifndef B200_NOINLINE_SD
+#define B200_NOINLINE_SD 0
+#endif
+#if B200_NOINLINE_SD
+#define B200_SD_INLINE __noinline__
+#else
+#define B200_SD_INLINE __forceinline__
+#endif
 template <bool LITERAL>
-__device__ __forceinline__ SDist sd_quadratic(const SegRec &s, d2 p, double need) {
+__device__ B200_SD_INLINE SDist sd_quadratic(const SegRec &s, d2 p, double need) {
     d2 qa = s.p0-p;
     d2 ab = mk(s.e[0], s.e[1]);
     d2 br = mk(s.e[2], s.e[3]);

@@ -495,8 +495,11 @@ __device__ __forceinline__ EcSpans ec_spans(const GlyphDesc &g, double minDeviat
 //      square roots, interpolations) that survive the exact prefilters into a tile-wide queue — about 0.4 per texel;
 //   2  the whole CTA runs the queued tests, 256 at a time with every lane busy, and ORs the verdicts into the owners' flags;
 //   3  apply (error texels <- median), stencil and the float4 write-back.
+#ifndef K2_MIN_CTAS
+#define K2_MIN_CTAS 3
+#endif
 template <int N>
-__global__ void __launch_bounds__(CTA_THREADS, 3) k2_classify(KernelParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, K2_MIN_CTAS) k2_classify(KernelParams P) {
     __shared__ int2 s_corner[SMEM_RECORDS];
     __shared__ __align__(16) float s_out[EC_WARPS][32*4];
     __shared__ GlyphDesc s_g;
