@@ -588,163 +588,173 @@ double polylineLength(const EdgeSegment *edge) {
     return total;
 }
 
-void paintSmoothContour(Contour &contour, ColorStream &stream) {
-    stream.advance();
-    for (size_t i = 0; i < contour.edges.size(); ++i)
-        contour.edges[i]->color = stream.color;
+// ---- the colouring of ONE closed contour, independent of what holds its geometry -------------------------------------------------
+// Both entry paths (Shape objects; flat arrays of a batch) reduce a contour to the unit tangents at the two ends of every edge
+// (tangents[2i] = direction(0).normalize(), tangents[2i+1] = direction(1).normalize() of edge i) and, for the ink-trap variant,
+// a length estimate per edge; colours go out through a callback.  Colour corners are where consecutive tangents turn sharply.
+struct ColorCorner {
+    int index;
+    double precedingLength;   // estimated length of the spline that ends at this corner (ink trap)
+    bool minor;
+    EdgeColor color;
+};
+
+// A contour with exactly one corner and fewer than three edges cannot carry three colours: the caller has to split its edges in
+// thirds first.  paintContour then only reports the corner and the three colours (the stream has been advanced).
+struct TeardropSplit {
+    bool needed;
+    int corner;
+    EdgeColor colors[3];
+};
+
+template <typename LengthOf, typename SetColor>
+TeardropSplit paintContour(int m, const Vector2 *tangents, int coloring, double crossThreshold, ColorStream &stream, std::vector<ColorCorner> &corners,
+                           LengthOf lengthOf, SetColor setColor) {
+    TeardropSplit split = { false, 0, { BLACK, BLACK, BLACK } };
+    double splineLength = 0;
+    corners.clear();
+    Vector2 inDir = tangents[2*(m-1)+1];
+    for (int i = 0; i < m; ++i) {
+        if (sharpCorner(inDir, tangents[2*i], crossThreshold)) {
+            ColorCorner corner = { i, splineLength, false, BLACK };
+            corners.push_back(corner);
+            splineLength = 0;
+        }
+        if (coloring == 2)
+            splineLength += lengthOf(i);
+        inDir = tangents[2*i+1];
+    }
+    const int cornerCount = (int) corners.size();
+    if (cornerCount == 0) {
+        // smooth loop: one colour
+        stream.advance();
+        for (int i = 0; i < m; ++i)
+            setColor(i, stream.color);
+    } else if (cornerCount == 1) {
+        // teardrop: three colours around the loop, white in the middle
+        stream.advance();
+        split.colors[0] = stream.color;
+        split.colors[1] = WHITE;
+        stream.advance();
+        split.colors[2] = stream.color;
+        split.corner = corners[0].index;
+        if (m >= 3) {
+            for (int i = 0; i < m; ++i)
+                setColor((split.corner+i)%m, split.colors[1+thirdOf(i, m)]);
+        } else
+            split.needed = true;
+    } else if (coloring == 1) {
+        // simple: a new colour at every corner; the last spline must also differ from the first
+        int spline = 0;
+        const int start = corners[0].index;
+        stream.advance();
+        const EdgeColor initialColor = stream.color;
+        for (int i = 0; i < m; ++i) {
+            const int index = (start+i)%m;
+            if (spline+1 < cornerCount && corners[spline+1].index == index) {
+                ++spline;
+                stream.advance(EdgeColor((spline == cornerCount-1)*initialColor));
+            }
+            setColor(index, stream.color);
+        }
+    } else {
+        // ink trap: corners that only enclose a short spline between two longer ones are "minor" and get the colour that
+        // differs from both neighbours, so that the short spline does not cost a colour change of its own
+        int majorCornerCount = cornerCount;
+        if (cornerCount > 3) {
+            corners[0].precedingLength += splineLength;
+            for (int i = 0; i < cornerCount; ++i) {
+                if (corners[i].precedingLength > corners[(i+1)%cornerCount].precedingLength &&
+                    corners[(i+1)%cornerCount].precedingLength < corners[(i+2)%cornerCount].precedingLength) {
+                    corners[i].minor = true;
+                    --majorCornerCount;
+                }
+            }
+        }
+        EdgeColor initialColor = BLACK;
+        for (int i = 0; i < cornerCount; ++i) {
+            if (!corners[i].minor) {
+                --majorCornerCount;
+                stream.advance(EdgeColor(!majorCornerCount*initialColor));
+                corners[i].color = stream.color;
+                if (!initialColor)
+                    initialColor = stream.color;
+            }
+        }
+        for (int i = 0; i < cornerCount; ++i) {
+            if (corners[i].minor) {
+                EdgeColor nextColor = corners[(i+1)%cornerCount].color;
+                corners[i].color = EdgeColor((stream.color&nextColor)^WHITE);
+            } else
+                stream.color = corners[i].color;
+        }
+        int spline = 0;
+        const int start = corners[0].index;
+        stream.color = corners[0].color;
+        for (int i = 0; i < m; ++i) {
+            const int index = (start+i)%m;
+            if (spline+1 < cornerCount && corners[spline+1].index == index)
+                stream.color = corners[++spline].color;
+            setColor(index, stream.color);
+        }
+    }
+    return split;
 }
 
-// One corner only: three colours around the loop, white in the middle; contours of 1-2 edges are split to make room.
-void paintTeardrop(Contour &contour, int corner, ColorStream &stream) {
-    EdgeColor colors[3];
-    stream.advance();
-    colors[0] = stream.color;
-    colors[1] = WHITE;
-    stream.advance();
-    colors[2] = stream.color;
+// One- or two-edge teardrop of a Shape: every edge becomes three, the six (or three) parts take the three colours in order
+// starting at the corner.
+void splitTeardrop(Contour &contour, const TeardropSplit &split) {
     std::vector<EdgeHolder> &edges = contour.edges;
-    if (edges.size() >= 3) {
-        int m = (int) edges.size();
-        for (int i = 0; i < m; ++i)
-            edges[(corner+i)%m]->color = colors[1+thirdOf(i, m)];
-    } else if (edges.size() >= 1) {
-        EdgeSegment *parts[7] = { };
-        edges[0]->splitInThirds(parts[0+3*corner], parts[1+3*corner], parts[2+3*corner]);
-        if (edges.size() >= 2) {
-            edges[1]->splitInThirds(parts[3-3*corner], parts[4-3*corner], parts[5-3*corner]);
-            parts[0]->color = parts[1]->color = colors[0];
-            parts[2]->color = parts[3]->color = colors[1];
-            parts[4]->color = parts[5]->color = colors[2];
-        } else {
-            parts[0]->color = colors[0];
-            parts[1]->color = colors[1];
-            parts[2]->color = colors[2];
+    EdgeSegment *parts[7] = { };
+    const int corner = split.corner;
+    edges[0]->splitInThirds(parts[0+3*corner], parts[1+3*corner], parts[2+3*corner]);
+    if (edges.size() >= 2) {
+        edges[1]->splitInThirds(parts[3-3*corner], parts[4-3*corner], parts[5-3*corner]);
+        for (int i = 0; i < 6; ++i)
+            parts[i]->color = split.colors[i/2];
+    } else {
+        for (int i = 0; i < 3; ++i)
+            parts[i]->color = split.colors[i];
+    }
+    edges.clear();
+    for (int i = 0; parts[i]; ++i)
+        edges.push_back(EdgeHolder(parts[i]));
+}
+
+// edgeColoringSimple (coloring 1) / edgeColoringInkTrap (2) of a Shape: the contours' tangents, then the shared core.
+void colorShape(Shape &shape, int coloring, double angleThreshold, unsigned long long seed) {
+    const double crossThreshold = std::sin(angleThreshold);
+    ColorStream stream(seed);
+    std::vector<ColorCorner> corners;
+    std::vector<Vector2> tangents;
+    for (size_t c = 0; c < shape.contours.size(); ++c) {
+        Contour &contour = shape.contours[c];
+        std::vector<EdgeHolder> &edges = contour.edges;
+        const int m = (int) edges.size();
+        if (m == 0)
+            continue;
+        tangents.resize(2*size_t(m));
+        for (int i = 0; i < m; ++i) {
+            tangents[2*size_t(i)] = edges[size_t(i)]->direction(0).normalize();
+            tangents[2*size_t(i)+1] = edges[size_t(i)]->direction(1).normalize();
         }
-        edges.clear();
-        for (int i = 0; parts[i]; ++i)
-            edges.push_back(EdgeHolder(parts[i]));
+        const TeardropSplit split = paintContour(m, tangents.data(), coloring, crossThreshold, stream, corners,
+            [&edges](int i) { return polylineLength(edges[size_t(i)]); },
+            [&edges](int i, EdgeColor color) { edges[size_t(i)]->color = color; });
+        if (split.needed)
+            splitTeardrop(contour, split);
     }
 }
 
 }  // namespace
 
-void edgeColoringSimple(Shape &shape, double angleThreshold, unsigned long long seed) {
-    double crossThreshold = std::sin(angleThreshold);
-    ColorStream stream(seed);
-    std::vector<int> corners;
-    for (size_t c = 0; c < shape.contours.size(); ++c) {
-        Contour &contour = shape.contours[c];
-        if (contour.edges.empty())
-            continue;
-        corners.clear();
-        Vector2 inDir = contour.edges.back()->direction(1);
-        for (size_t i = 0; i < contour.edges.size(); ++i) {
-            if (sharpCorner(inDir.normalize(), contour.edges[i]->direction(0).normalize(), crossThreshold))
-                corners.push_back((int) i);
-            inDir = contour.edges[i]->direction(1);
-        }
-        if (corners.empty())
-            paintSmoothContour(contour, stream);
-        else if (corners.size() == 1)
-            paintTeardrop(contour, corners[0], stream);
-        else {
-            int cornerCount = (int) corners.size();
-            int spline = 0;
-            int start = corners[0];
-            int m = (int) contour.edges.size();
-            stream.advance();
-            EdgeColor initialColor = stream.color;
-            for (int i = 0; i < m; ++i) {
-                int index = (start+i)%m;
-                if (spline+1 < cornerCount && corners[spline+1] == index) {
-                    ++spline;
-                    stream.advance(EdgeColor((spline == cornerCount-1)*initialColor));
-                }
-                contour.edges[index]->color = stream.color;
-            }
-        }
-    }
-}
-
-void edgeColoringInkTrap(Shape &shape, double angleThreshold, unsigned long long seed) {
-    struct Corner {
-        int index;
-        double precedingLength;   // estimated length of the spline that ends at this corner
-        bool minor;
-        EdgeColor color;
-    };
-    double crossThreshold = std::sin(angleThreshold);
-    ColorStream stream(seed);
-    std::vector<Corner> corners;
-    for (size_t c = 0; c < shape.contours.size(); ++c) {
-        Contour &contour = shape.contours[c];
-        if (contour.edges.empty())
-            continue;
-        double splineLength = 0;
-        corners.clear();
-        Vector2 inDir = contour.edges.back()->direction(1);
-        for (size_t i = 0; i < contour.edges.size(); ++i) {
-            if (sharpCorner(inDir.normalize(), contour.edges[i]->direction(0).normalize(), crossThreshold)) {
-                Corner corner = { (int) i, splineLength, false, BLACK };
-                corners.push_back(corner);
-                splineLength = 0;
-            }
-            splineLength += polylineLength(contour.edges[i]);
-            inDir = contour.edges[i]->direction(1);
-        }
-        if (corners.empty())
-            paintSmoothContour(contour, stream);
-        else if (corners.size() == 1)
-            paintTeardrop(contour, corners[0].index, stream);
-        else {
-            int cornerCount = (int) corners.size();
-            int majorCornerCount = cornerCount;
-            if (cornerCount > 3) {
-                corners[0].precedingLength += splineLength;
-                // a corner is "minor" when the spline after it is shorter than both of that spline's neighbours
-                for (int i = 0; i < cornerCount; ++i) {
-                    if (corners[i].precedingLength > corners[(i+1)%cornerCount].precedingLength &&
-                        corners[(i+1)%cornerCount].precedingLength < corners[(i+2)%cornerCount].precedingLength) {
-                        corners[i].minor = true;
-                        --majorCornerCount;
-                    }
-                }
-            }
-            EdgeColor initialColor = BLACK;
-            for (int i = 0; i < cornerCount; ++i) {
-                if (!corners[i].minor) {
-                    --majorCornerCount;
-                    stream.advance(EdgeColor(!majorCornerCount*initialColor));
-                    corners[i].color = stream.color;
-                    if (!initialColor)
-                        initialColor = stream.color;
-                }
-            }
-            for (int i = 0; i < cornerCount; ++i) {
-                if (corners[i].minor) {
-                    EdgeColor nextColor = corners[(i+1)%cornerCount].color;
-                    corners[i].color = EdgeColor((stream.color&nextColor)^WHITE);
-                } else
-                    stream.color = corners[i].color;
-            }
-            int spline = 0;
-            int start = corners[0].index;
-            stream.color = corners[0].color;
-            int m = (int) contour.edges.size();
-            for (int i = 0; i < m; ++i) {
-                int index = (start+i)%m;
-                if (spline+1 < cornerCount && corners[spline+1].index == index)
-                    stream.color = corners[++spline].color;
-                contour.edges[index]->color = stream.color;
-            }
-        }
-    }
-}
+void edgeColoringSimple(Shape &shape, double angleThreshold, unsigned long long seed) { colorShape(shape, 1, angleThreshold, seed); }
+void edgeColoringInkTrap(Shape &shape, double angleThreshold, unsigned long long seed) { colorShape(shape, 2, angleThreshold, seed); }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Allocation-free preparation of one glyph on flat arrays (flat_prep.h).  Segments are materialised as STACK objects of the
-// same classes the Shape path uses, so every direction / point / length is computed by the very same member functions; the
-// colouring logic below is the one above with `contour.edges[i]->color = c` replaced by `outColors[first+i] = c`.
+// same classes the Shape path uses, so every direction / point / length is computed by the very same member functions, and the
+// colours come from the same paintContour as the Shape path's.
 
 namespace b200 {
 
@@ -815,13 +825,7 @@ bool prepareGlyphFlat(const uint32_t *cbegin, uint32_t c0, uint32_t c1, const do
             outColors[s] = inColors ? inColors[s] : (uint8_t) WHITE;
         return true;
     }
-    struct Corner {
-        int index;
-        double precedingLength;
-        bool minor;
-        EdgeColor color;
-    };
-    static thread_local std::vector<Corner> corners;
+    static thread_local std::vector<ColorCorner> corners;
     ColorStream stream(seed);
     for (uint32_t c = c0; c < c1; ++c) {
         const uint32_t first = cbegin[c];
@@ -829,85 +833,10 @@ bool prepareGlyphFlat(const uint32_t *cbegin, uint32_t c0, uint32_t c1, const do
         if (m == 0)
             continue;
         uint8_t *colors = outColors+first;
-        double splineLength = 0;
-        corners.clear();
-        Vector2 inDir = tangents[2*size_t(first+m-1-s0)+1];
-        for (int i = 0; i < m; ++i) {
-            if (sharpCorner(inDir, tangents[2*size_t(first+i-s0)], crossThreshold)) {
-                Corner corner = { i, splineLength, false, BLACK };
-                corners.push_back(corner);
-                splineLength = 0;
-            }
-            if (coloring == 2)
-                splineLength += StackEdge(points+8*size_t(first+i), orders[first+i]).polylineLength();
-            inDir = tangents[2*size_t(first+i-s0)+1];
-        }
-        const int cornerCount = (int) corners.size();
-        if (cornerCount == 0) {                 // paintSmoothContour
-            stream.advance();
-            for (int i = 0; i < m; ++i)
-                colors[i] = (uint8_t) stream.color;
-        } else if (cornerCount == 1) {          // paintTeardrop, m >= 3
-            EdgeColor three[3];
-            stream.advance();
-            three[0] = stream.color;
-            three[1] = WHITE;
-            stream.advance();
-            three[2] = stream.color;
-            for (int i = 0; i < m; ++i)
-                colors[(corners[0].index+i)%m] = (uint8_t) three[1+thirdOf(i, m)];
-        } else if (coloring == 1) {             // edgeColoringSimple
-            int spline = 0;
-            const int start = corners[0].index;
-            stream.advance();
-            const EdgeColor initialColor = stream.color;
-            for (int i = 0; i < m; ++i) {
-                const int index = (start+i)%m;
-                if (spline+1 < cornerCount && corners[spline+1].index == index) {
-                    ++spline;
-                    stream.advance(EdgeColor((spline == cornerCount-1)*initialColor));
-                }
-                colors[index] = (uint8_t) stream.color;
-            }
-        } else {                                // edgeColoringInkTrap
-            int majorCornerCount = cornerCount;
-            if (cornerCount > 3) {
-                corners[0].precedingLength += splineLength;
-                for (int i = 0; i < cornerCount; ++i) {
-                    if (corners[i].precedingLength > corners[(i+1)%cornerCount].precedingLength &&
-                        corners[(i+1)%cornerCount].precedingLength < corners[(i+2)%cornerCount].precedingLength) {
-                        corners[i].minor = true;
-                        --majorCornerCount;
-                    }
-                }
-            }
-            EdgeColor initialColor = BLACK;
-            for (int i = 0; i < cornerCount; ++i) {
-                if (!corners[i].minor) {
-                    --majorCornerCount;
-                    stream.advance(EdgeColor(!majorCornerCount*initialColor));
-                    corners[i].color = stream.color;
-                    if (!initialColor)
-                        initialColor = stream.color;
-                }
-            }
-            for (int i = 0; i < cornerCount; ++i) {
-                if (corners[i].minor) {
-                    EdgeColor nextColor = corners[(i+1)%cornerCount].color;
-                    corners[i].color = EdgeColor((stream.color&nextColor)^WHITE);
-                } else
-                    stream.color = corners[i].color;
-            }
-            int spline = 0;
-            const int start = corners[0].index;
-            stream.color = corners[0].color;
-            for (int i = 0; i < m; ++i) {
-                const int index = (start+i)%m;
-                if (spline+1 < cornerCount && corners[spline+1].index == index)
-                    stream.color = corners[++spline].color;
-                colors[index] = (uint8_t) stream.color;
-            }
-        }
+        // (pass 1 has sent every contour that would need the teardrop split down the general path)
+        paintContour(m, &tangents[2*size_t(first-s0)], coloring, crossThreshold, stream, corners,
+            [=](int i) { return StackEdge(points+8*size_t(first+i), orders[first+i]).polylineLength(); },
+            [=](int i, EdgeColor color) { colors[i] = (uint8_t) color; });
     }
     return true;
 }

@@ -14,7 +14,8 @@ import numpy as np
 from .flat import FlatShapes
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-HOST_LIB_PATH = os.path.join(HERE, "libmsdfgen_b200_host.so")
+# B200MSDF_HOST_LIB selects an alternative build of the SAME host library (development); default is the in-tree build.
+HOST_LIB_PATH = os.environ.get("B200MSDF_HOST_LIB") or os.path.join(HERE, "libmsdfgen_b200_host.so")
 _host = None
 
 COLORING = {None: 0, "none": 0, "simple": 1, "inktrap": 2}
