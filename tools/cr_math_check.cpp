@@ -1,5 +1,6 @@
 // Host check of msdfgen_b200/csrc/cr_math.cuh against quad precision (libquadmath): every result must be the correctly rounded
-// double.  Build: g++ -O2 -ffp-contract=off -o /tmp/cr_math_check tools/cr_math_check.cpp -lquadmath ; run: /tmp/cr_math_check
+// double.  Build: g++ -O2 -ffp-contract=off -o /tmp/cr_math_check tools/cr_math_check.cpp -lquadmath ; run: /tmp/cr_math_check [samples]
+// (tests/test_cr_math.py runs it with 300 000 samples per function)
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -7,11 +8,11 @@
 #include <quadmath.h>
 #include "../msdfgen_b200/csrc/cr_math.cuh"
 
-int main() {
+int main(int argc, char **argv) {
     std::mt19937_64 rng(12345);
     std::uniform_real_distribution<double> u(0, 1);
     long bad[3] = { 0, 0, 0 }, libm[3] = { 0, 0, 0 };
-    const long N = 4000000;
+    const long N = argc > 1 ? atol(argv[1]) : 4000000;
     for (long i = 0; i < N; ++i) {
         // acos: mix of uniform arguments and arguments crowding the ends
         double x = 2*u(rng)-1;
