@@ -396,6 +396,22 @@ def test_misaligned_pinned_block_and_bad_orders(ctx):
         ctx.generate_batch(api.MSDF, want, bad, xf)
 
 
+def test_small_glyphs_with_many_contours(ctx, port):
+    """Glyphs that fit the shared-memory record path (<= 96 segments) but have more contours than the per-thread contour store
+    holds (4): the overlapping combiner's parked state goes through the global scratch slices.  Every mode, both combiners."""
+    shapes = [prep.prepare(synth_big_shape(8, 8, seed=s)) for s in (1, 2)] + [prep.prepare(synth_big_shape(12, 7, seed=3))]
+    for shape in shapes:
+        assert shape.n_segments <= 96 and shape.n_contours > 4
+        cb, p, od, cl, _ = shape.glyph(0)
+        for mode_name, mode in MODE.items():
+            for overlap in (True, False):
+                xf = glyph_transform(40, px_range=6.0)
+                cfg = api.MSDFGeneratorConfig(overlapSupport=overlap)
+                got = np.full((40, 40, api.CHANNELS[mode]), np.nan, np.float32)
+                ctx.generate(mode, got, shape, xf, cfg)
+                assert_parity(got, port.generate(mode_name, cb, p, od, cl, xf, 40, 40, _ocfg(cfg)), f"{mode_name} overlap={overlap}")
+
+
 def test_regions_reject_error_correction(ctx):
     g = prep.prepare(synth_glyph(3))
     b = ctx.upload(api.MSDF, g, glyph_transform(16), [16, 8], origins=[0, 4])
