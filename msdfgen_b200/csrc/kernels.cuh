@@ -566,17 +566,6 @@ __global__ void __launch_bounds__(K1_THREADS, K1B_MIN_CTAS) k1b_exact(KernelPara
                 if (valid)
                     texel_literal<MODE, OVERLAP>(s_recs, nRec, p.x, p.y, store, s_g.dmScale, s_g.dmTranslate, &s_out[warp][lane*NOUT]);
             }
-#elif B200_GUARD_MODE == 2
-            if (guard_flag()) {
-                // guard band hit: the recheck launch (k1_distance_field<.., true>) recomputes this texel with the literal solver
-                guard_flag() = 0;
-                if (valid) {
-                    const size_t t = size_t(s_g.texelOffset)+size_t(yOut)*w+x;
-                    atomicOr(&P.recheckMask[t>>5], 1u<<(t&31));
-                    P.recheckTiles[tile] = 1;
-                    *P.recheckAny = 1;
-                }
-            }
 #endif
             __syncwarp();
             if (grid.blocked) {
@@ -597,6 +586,21 @@ __global__ void __launch_bounds__(K1_THREADS, K1B_MIN_CTAS) k1b_exact(KernelPara
                     dst[i] = s_out[warp][i];
             }
             __syncwarp();
+#if B200_GUARD_MODE == 2
+            // guard band hit by some lane (rare): record the texel for the recheck launch (k1_distance_field<.., true>), which
+            // recomputes it with the literal solver.  The texel is re-derived from (unit, lane) here, so that nothing extra has
+            // to stay live across exact_texel (keeping x, yOut and the tile index alive there cost 0.2 ms per atlas).
+            if (__any_sync(0xffffffffu, guard_flag() != 0) && guard_flag()) {
+                guard_flag() = 0;
+                int fx, fy;
+                if (grid.texel(s_g, td, u, lane, fx, fy)) {
+                    const size_t t = size_t(s_g.texelOffset)+size_t(fy)*s_g.w+fx;
+                    atomicOr(&P.recheckMask[t>>5], 1u<<(t&31));
+                    P.recheckTiles[s_tile] = 1;
+                    *P.recheckAny = 1;
+                }
+            }
+#endif
         }
     }
 }

@@ -87,3 +87,13 @@ def test_literal_solver_is_rare_on_ordinary_glyphs_and_used_on_cusps(ctx):
     f = np.empty((h, w, 1), np.float32)
     ctx.generate(api.SDF, f, FlatShapes.single(cb, pts, od, cl), xf)
     assert ctx.exact_root_calls(reset=True) > 0
+    # family 1: straight-line quadratics on the integer grid with texel centres on integer coordinates — foot points fall exactly
+    # on end points, i.e. roots at 0 and 1: the guard band's home turf (these shapes carry no cusp segments, so every run of the
+    # literal solver counted here comes from the recheck launch; their digests are checked by test_cuda_matches_reference_digests)
+    grid = 0
+    for seed in (1, 10, 19, 28):
+        fam, cb, pts, od, cl, xf, w, h = fuzz_shape(seed)
+        f = np.empty((h, w, 3), np.float32)
+        ctx.generate(api.MSDF, f, FlatShapes.single(cb, pts, od, cl), xf)
+        grid += ctx.exact_root_calls(reset=True)
+    print(f"[guard band] literal-solver runs on four grid-aligned straight-quadratic shapes: {grid}")
