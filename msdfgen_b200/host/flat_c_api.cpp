@@ -1,7 +1,7 @@
 // flat_c_api.cpp — extern "C" access to the host shape preparation for callers that keep shapes as flat arrays
-// (the Python package, bench.py): builds msdfgen::Shape objects from a flat batch, runs Shape::normalize() and an edge
-// colouring on every glyph, and flattens the result again.  Host-only (no device work); this is the batch-ingest step that
-// precedes b200msdf_generate_batch (SURVEY.md §8f "next" #1).
+// (the Python package, bench.py): Shape::normalize() and an edge colouring for every glyph of a flat batch, computed on the
+// arrays themselves (flat_prep.h) — no msdfgen::Shape is built unless B200MSDF_HOST_FLAT=0 asks for the object path.
+// Host-only (no device work); this is the batch-ingest step that precedes b200msdf_generate_batch (SURVEY.md §8f "next" #1).
 #include "msdfgen.h"
 #include "flat_prep.h"
 
@@ -33,10 +33,9 @@ void buildShape(Shape &shape, const uint32_t *cbegin, uint32_t c0, uint32_t c1, 
 }
 
 // Glyphs are independent, so the batch entry points split [0, n) into contiguous ranges over host threads (the GPU needs
-// ~1.2 us per glyph; preparation costs ~5 us per glyph of CPU time plus as much again in allocator work, which would make it
-// the slowest stage of an atlas build).  At most 16 threads by default; B200MSDF_HOST_THREADS overrides the count.  Measured in
-// the 8-vCPU build container on 4096 glyphs: prepare 22 -> 5 ms, flatten 3 -> 1 ms, teardown 8 -> 5 ms with a warm heap; with a
-// cold heap (fresh output arrays every call) the page faults of the allocator dominate and the split gains nothing.
+// ~1.1 us per glyph; preparation costs ~2 us per glyph of CPU time, which alone would make it the slowest stage of an atlas
+// build).  At most 16 threads by default; B200MSDF_HOST_THREADS overrides the count.  Measured in the 8-vCPU build container on
+// 4096 glyphs (begin + fetch): 8.5 ms on one thread, 3.1 ms on eight.
 template <typename F>
 void parallelRanges(size_t n, size_t grain, F body) {
     size_t threads = std::thread::hardware_concurrency();
@@ -63,13 +62,16 @@ void parallelRanges(size_t n, size_t grain, F body) {
 
 extern "C" {
 
-/// Pass 1 of 2: prepares every glyph and returns the totals needed to size the output arrays. The prepared shapes are kept
-/// in an opaque handle until b200host_prepare_fetch / b200host_prepare_free.
+/// Pass 1 of 2: prepares every glyph and returns the totals needed to size the output arrays.  Glyphs whose geometry changed
+/// are kept (as flat segment lists) in an opaque handle until b200host_prepare_fetch / b200host_prepare_free.
 struct b200host_prepared {
-    std::vector<Shape> shapes;          // glyphs that went through the general path (empty Shape for the others)
-    std::vector<uint8_t> flat;          // 1: the glyph's geometry is unchanged, only colours were computed (flatColors)
-    std::vector<uint8_t> flatColors;    // per input segment
-    // the caller's input arrays: flat glyphs are copied from them by b200host_prepare_fetch, so they must stay alive until then
+    struct Changed {
+        std::vector<flat::Seg> segs;
+        std::vector<uint32_t> cbegin;       // local contour offsets into segs, from 0
+    };
+    std::vector<Changed> changed;       // per glyph; empty cbegin = the glyph's geometry is unchanged, only colours were computed
+    std::vector<uint8_t> flatColors;    // per input segment (unchanged glyphs)
+    // the caller's input arrays: unchanged glyphs are copied from them by b200host_prepare_fetch, so they must stay alive until then
     const uint32_t *gbegin, *cbegin;
     const double *points;
     const uint8_t *orders;
@@ -79,21 +81,23 @@ int b200host_prepare_begin(int nGlyphs, const uint32_t *gbegin, const uint32_t *
                            const uint8_t *yDown, int doNormalize, int coloring, double angleThreshold, unsigned long long seed,
                            b200host_prepared **handle, int *outContours, int *outSegments) {
     b200host_prepared *h = new b200host_prepared;
-    h->shapes.resize((size_t) nGlyphs);
-    h->flat.assign((size_t) nGlyphs, 0);
+    h->changed.resize((size_t) nGlyphs);
     h->flatColors.resize(nGlyphs > 0 ? (size_t) cbegin[gbegin[nGlyphs]] : 0);
     h->gbegin = gbegin; h->cbegin = cbegin; h->points = points; h->orders = orders;
-    // B200MSDF_HOST_FLAT=0 forces every glyph through the Shape objects (for testing the two paths against each other)
+    // B200MSDF_HOST_FLAT=0 sends every glyph through the msdfgen-compatible Shape objects instead (Shape::normalize,
+    // edgeColoring*): the two entry paths share their algorithms but not their plumbing, and tests compare them
     const char *flatEnv = std::getenv("B200MSDF_HOST_FLAT");
-    const bool tryFlat = !(flatEnv && flatEnv[0] == '0');
+    const bool viaObjects = flatEnv && flatEnv[0] == '0';
     parallelRanges((size_t) nGlyphs, 64, [&](size_t g0, size_t g1) {
         for (size_t g = g0; g < g1; ++g) {
-            // almost every glyph keeps its geometry: colours are then computed straight from the flat arrays, no allocation
-            if (tryFlat && b200::prepareGlyphFlat(cbegin, gbegin[g], gbegin[g+1], points, orders, colors, doNormalize != 0, coloring, angleThreshold, seed, h->flatColors.data())) {
-                h->flat[g] = 1;
+            b200host_prepared::Changed &out = h->changed[g];
+            if (!viaObjects) {
+                // almost every glyph keeps its geometry: colours are then computed straight from the arrays, no allocation
+                flat::prepareGlyph(cbegin, gbegin[g], gbegin[g+1], points, orders, colors, doNormalize != 0, coloring, angleThreshold, seed,
+                                   h->flatColors.data(), out.segs, out.cbegin);
                 continue;
             }
-            Shape &shape = h->shapes[g];
+            Shape shape;
             buildShape(shape, cbegin, gbegin[g], gbegin[g+1], points, orders, colors, yDown ? yDown[g] != 0 : false);
             if (doNormalize)
                 shape.normalize();
@@ -101,16 +105,27 @@ int b200host_prepare_begin(int nGlyphs, const uint32_t *gbegin, const uint32_t *
                 edgeColoringSimple(shape, angleThreshold, seed);
             else if (coloring == 2)
                 edgeColoringInkTrap(shape, angleThreshold, seed);
+            out.cbegin.push_back(0);
+            for (size_t ci = 0; ci < shape.contours.size(); ++ci) {
+                const std::vector<EdgeHolder> &edges = shape.contours[ci].edges;
+                for (size_t i = 0; i < edges.size(); ++i) {
+                    const Point2 *cp = edges[i]->controlPoints();
+                    const int order = edges[i]->type();
+                    out.segs.push_back(flat::makeSeg(order, cp[0], cp[1], order >= 2 ? cp[2] : Point2(), order >= 3 ? cp[3] : Point2(), edges[i]->color));
+                }
+                out.cbegin.push_back((uint32_t) out.segs.size());
+            }
         }
     });
     int nc = 0, ns = 0;
     for (int g = 0; g < nGlyphs; ++g) {
-        if (h->flat[(size_t) g]) {
+        const b200host_prepared::Changed &out = h->changed[(size_t) g];
+        if (out.cbegin.empty()) {
             nc += (int) (gbegin[g+1]-gbegin[g]);
             ns += (int) (cbegin[gbegin[g+1]]-cbegin[gbegin[g]]);
         } else {
-            nc += (int) h->shapes[(size_t) g].contours.size();
-            ns += h->shapes[(size_t) g].edgeCount();
+            nc += (int) out.cbegin.size()-1;
+            ns += (int) out.segs.size();
         }
     }
     *handle = h;
@@ -120,68 +135,45 @@ int b200host_prepare_begin(int nGlyphs, const uint32_t *gbegin, const uint32_t *
 }
 
 int b200host_prepare_fetch(b200host_prepared *h, uint32_t *gbegin, uint32_t *cbegin, double *points, uint8_t *orders, uint8_t *colors) {
-    // offsets first (serial, O(glyphs)), then every thread flattens its own glyph range
-    const size_t n = h->shapes.size();
+    // offsets first (serial, O(glyphs)), then every thread writes its own glyph range
+    const size_t n = h->changed.size();
     std::vector<uint32_t> segBegin(n+1, 0);
     gbegin[0] = 0;
     cbegin[0] = 0;
     for (size_t g = 0; g < n; ++g) {
-        if (h->flat[g]) {
+        const b200host_prepared::Changed &out = h->changed[g];
+        if (out.cbegin.empty()) {
             gbegin[g+1] = gbegin[g]+(h->gbegin[g+1]-h->gbegin[g]);
             segBegin[g+1] = segBegin[g]+(h->cbegin[h->gbegin[g+1]]-h->cbegin[h->gbegin[g]]);
         } else {
-            gbegin[g+1] = gbegin[g]+(uint32_t) h->shapes[g].contours.size();
-            segBegin[g+1] = segBegin[g]+(uint32_t) h->shapes[g].edgeCount();
+            gbegin[g+1] = gbegin[g]+(uint32_t) out.cbegin.size()-1;
+            segBegin[g+1] = segBegin[g]+(uint32_t) out.segs.size();
         }
     }
     parallelRanges(n, 64, [&](size_t g0, size_t g1) {
-    for (size_t g = g0; g < g1; ++g) {
-        uint32_t c = gbegin[g], s = segBegin[g];
-        if (h->flat[g]) {
-            // unchanged geometry: block copy of the input segments (unused control-point slots zeroed like the general path)
-            const uint32_t ic0 = h->gbegin[g], ic1 = h->gbegin[g+1];
-            const uint32_t is0 = h->cbegin[ic0], is1 = h->cbegin[ic1];
-            for (uint32_t ic = ic0; ic < ic1; ++ic)
-                cbegin[++c] = s+(h->cbegin[ic+1]-is0);
-            for (uint32_t is = is0; is < is1; ++is, ++s) {
-                const int order = h->orders[is];
-                for (int k = 0; k < 8; ++k)
-                    points[8*size_t(s)+k] = k < 2*(order+1) ? h->points[8*size_t(is)+k] : 0;
-                orders[s] = h->orders[is];
-                colors[s] = h->flatColors[is];
+        for (size_t g = g0; g < g1; ++g) {
+            const b200host_prepared::Changed &out = h->changed[g];
+            uint32_t c = gbegin[g], s = segBegin[g];
+            if (out.cbegin.empty()) {
+                // unchanged geometry: the input segments with their new colours (unused control-point slots zeroed)
+                const uint32_t ic0 = h->gbegin[g], ic1 = h->gbegin[g+1];
+                const uint32_t is0 = h->cbegin[ic0], is1 = h->cbegin[ic1];
+                for (uint32_t ic = ic0; ic < ic1; ++ic)
+                    cbegin[++c] = s+(h->cbegin[ic+1]-is0);
+                for (uint32_t is = is0; is < is1; ++is, ++s)
+                    flat::storeSeg(flat::loadSeg(h->points, h->orders, h->flatColors.data(), is), points, orders, colors, s);
+                continue;
             }
-            continue;
+            for (size_t ci = 0; ci+1 < out.cbegin.size(); ++ci)
+                cbegin[++c] = s+out.cbegin[ci+1];
+            for (size_t i = 0; i < out.segs.size(); ++i)
+                flat::storeSeg(out.segs[i], points, orders, colors, s+i);
         }
-        const Shape &shape = h->shapes[g];
-        for (size_t ci = 0; ci < shape.contours.size(); ++ci) {
-            const std::vector<EdgeHolder> &edges = shape.contours[ci].edges;
-            for (size_t i = 0; i < edges.size(); ++i) {
-                const EdgeSegment *edge = edges[i];
-                int order = edge->type();
-                const Point2 *cp = edge->controlPoints();
-                for (int k = 0; k < 4; ++k) {
-                    points[8*size_t(s)+2*k] = k <= order ? cp[k].x : 0;
-                    points[8*size_t(s)+2*k+1] = k <= order ? cp[k].y : 0;
-                }
-                orders[s] = (uint8_t) order;
-                colors[s] = (uint8_t) edge->color;
-                ++s;
-            }
-            cbegin[++c] = s;
-        }
-    }
     });
     return 0;
 }
 
 void b200host_prepare_free(b200host_prepared *h) {
-    if (!h)
-        return;
-    // tearing down ~36 heap-allocated segments per glyph is as expensive as building them: same split over threads
-    parallelRanges(h->shapes.size(), 64, [&](size_t g0, size_t g1) {
-        for (size_t g = g0; g < g1; ++g)
-            std::vector<Contour>().swap(h->shapes[g].contours);
-    });
     delete h;
 }
 

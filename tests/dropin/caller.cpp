@@ -158,6 +158,118 @@ int caller_estimate(int nContours, const uint32_t *cbegin, const double *pts, co
     return 0;
 }
 
+// The shape data model as a user sees it (no generator involved, host only): every member function of the edge, contour and
+// shape objects that returns geometry, probed on the caller's shape.  out receives a stream of doubles (cap of them at most);
+// returns how many were written, or -1 if cap is too small.  `raw` builds the edges without the factory's order lowering.
+namespace {
+struct Stream {
+    double *out; int cap, n;
+    void put(double v) { if (n < cap) out[n] = v; ++n; }
+    void put(Vector2 v) { put(v.x); put(v.y); }
+    void put(const EdgeSegment *e) {
+        put((double) e->type());
+        put((double) (int) e->color);
+        for (int i = 0; i <= e->type(); ++i)
+            put(e->controlPoints()[i]);
+    }
+};
+}
+
+int caller_shape_model(int nContours, const uint32_t *cbegin, const double *pts, const uint8_t *orders, int raw, double *out, int cap) {
+    static const double params[] = { 0, .25, 1/3., .5, .8125, 1 };
+    Stream o = { out, cap, 0 };
+    Shape shape;
+    if (raw) {
+        for (int c = 0; c < nContours; ++c) {
+            Contour &contour = shape.addContour();
+            for (uint32_t s = cbegin[c]; s < cbegin[c+1]; ++s) {
+                const double *p = pts+8*s;
+                if (orders[s] == 1)
+                    contour.addEdge(EdgeHolder(new LinearSegment(Point2(p[0], p[1]), Point2(p[2], p[3]), YELLOW)));
+                else if (orders[s] == 2)
+                    contour.addEdge(EdgeHolder(new QuadraticSegment(Point2(p[0], p[1]), Point2(p[2], p[3]), Point2(p[4], p[5]), CYAN)));
+                else
+                    contour.addEdge(EdgeHolder(new CubicSegment(Point2(p[0], p[1]), Point2(p[2], p[3]), Point2(p[4], p[5]), Point2(p[6], p[7]), MAGENTA)));
+            }
+        }
+    } else
+        buildShape(shape, nContours, cbegin, pts, orders, 0);
+    o.put((double) shape.validate());
+    o.put((double) shape.edgeCount());
+    for (size_t c = 0; c < shape.contours.size(); ++c) {
+        const Contour &contour = shape.contours[c];
+        o.put((double) contour.winding());
+        for (size_t i = 0; i < contour.edges.size(); ++i) {
+            const EdgeSegment *edge = contour.edges[i];
+            o.put(edge);
+            for (size_t k = 0; k < sizeof(params)/sizeof(*params); ++k) {
+                o.put(edge->point(params[k]));
+                o.put(edge->direction(params[k]));
+                o.put(edge->directionChange(params[k]));
+            }
+            double box[4] = { 1e9, 1e9, -1e9, -1e9 };
+            edge->bound(box[0], box[1], box[2], box[3]);
+            for (int k = 0; k < 4; ++k)
+                o.put(box[k]);
+            if (edge->type() == (int) LinearSegment::EDGE_TYPE)
+                o.put(static_cast<const LinearSegment *>(edge)->length());
+            if (edge->type() == (int) QuadraticSegment::EDGE_TYPE) {
+                o.put(static_cast<const QuadraticSegment *>(edge)->length());
+                EdgeHolder cubic(static_cast<const QuadraticSegment *>(edge)->convertToCubic());
+                o.put(cubic);
+            }
+            EdgeSegment *parts[3] = { };
+            edge->splitInThirds(parts[0], parts[1], parts[2]);
+            for (int k = 0; k < 3; ++k) {
+                o.put(parts[k]);
+                delete parts[k];
+            }
+            // edits on copies (EdgeHolder's copy is deep)
+            const Point2 target = edge->point(.5)+Vector2(.375, -.25);
+            EdgeHolder a(contour.edges[i]), b(contour.edges[i]), r = contour.edges[i];
+            a->moveStartPoint(target);
+            b->moveEndPoint(target);
+            r->reverse();
+            o.put(a); o.put(b); o.put(r);
+            o.put(edge);    // the original is untouched
+        }
+        for (int polarity = -1; polarity <= 1; ++polarity) {
+            double box[4] = { 1e9, 1e9, -1e9, -1e9 };
+            contour.bound(box[0], box[1], box[2], box[3]);
+            contour.boundMiters(box[0], box[1], box[2], box[3], .5, 2.5, polarity);
+            for (int k = 0; k < 4; ++k)
+                o.put(box[k]);
+        }
+        Contour reversed(contour);
+        reversed.reverse();
+        o.put((double) reversed.winding());
+        for (size_t i = 0; i < reversed.edges.size(); ++i)
+            o.put(reversed.edges[i]);
+    }
+    if (shape.edgeCount()) {
+        const Shape::Bounds plain = shape.getBounds(), wide = shape.getBounds(.25), mitered = shape.getBounds(.25, 3, 1);
+        const Shape::Bounds *all[3] = { &plain, &wide, &mitered };
+        for (int k = 0; k < 3; ++k) {
+            o.put(all[k]->l); o.put(all[k]->b); o.put(all[k]->r); o.put(all[k]->t);
+        }
+    }
+    // preparation through the objects, both colouring strategies
+    for (int strategy = 1; strategy <= 2; ++strategy) {
+        Shape prepared(shape);
+        prepared.normalize();
+        if (strategy == 1)
+            edgeColoringSimple(prepared, 3.0, 5);
+        else
+            edgeColoringInkTrap(prepared, 3.0, 5);
+        o.put((double) prepared.edgeCount());
+        for (size_t c = 0; c < prepared.contours.size(); ++c)
+            for (size_t i = 0; i < prepared.contours[c].edges.size(); ++i)
+                o.put(prepared.contours[c].edges[i]);
+    }
+    return o.n <= cap ? o.n : -1;
+}
+
+
 // Re-entrancy (the reference's generators are free functions without shared state, msdfgen.h:47-69): nThreads host threads
 // generate concurrently, each its own Shape object and its own bitmap of its own size (w+thread, h+thread), `reps` times.
 // out: the threads' [h+t][w+t][3] images back to back.  Returns the number of generator calls made.

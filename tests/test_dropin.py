@@ -76,6 +76,31 @@ def test_caller_compiles_against_both_interfaces():
     _build_ref()
 
 
+def _model(lib, g, raw):
+    cap = 400 * (len(g.orders) + 8)
+    out = np.full(cap, np.nan, np.float64)
+    n = lib.caller_shape_model(*_args(g), C.c_int(raw), out.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(cap))
+    assert n > 0
+    return out[:n].view(np.uint64)
+
+
+def test_shape_object_model_matches_reference(ref):
+    """The host mirror's Shape / Contour / EdgeSegment objects answer every geometric query of the msdfgen API (point, direction,
+    directionChange, bound, length, splitInThirds, convertToCubic, move*Point, reverse, winding, boundMiters, getBounds, normalize,
+    both colourings) with the reference's doubles, bit for bit — on ordinary glyphs, on cusps / teardrops / degenerate curves, and
+    with edges built past the factory (raw=1: no order lowering).  No device involved."""
+    from test_host_model import _cusp_shapes
+    from util import fuzz_shape
+    from msdfgen_b200.flat import FlatShapes
+    mine, theirs = _build_b200(), _build_ref()
+    shapes = [synth_glyph(200 + i, cubic_fraction=0.4 if i % 2 else 0.0) for i in range(12)] + _cusp_shapes()
+    shapes += [FlatShapes.single(*fuzz_shape(seed)[1:5]) for seed in range(0, 108, 5)]
+    for g in shapes:
+        for raw in (0, 1):
+            a, b = _model(mine, g, raw), _model(theirs, g, raw)
+            assert a.shape == b.shape and np.array_equal(a, b), (raw, int(np.argmax(a != b)) if a.shape == b.shape else (a.shape, b.shape))
+
+
 def test_reference_build_runs(ref):
     lib = _build_ref()
     r = _run(lib, synth_glyph(123, cubic_fraction=0.2))

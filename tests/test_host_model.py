@@ -89,9 +89,9 @@ def test_bounds():
 
 
 def test_flat_preparation_path_equals_shape_path():
-    """libmsdfgen_b200_host prepares glyphs whose geometry the preparation leaves untouched straight from the flat arrays
-    (host/flat_prep.h: no Shape objects, no allocation) and falls back to the Shape member functions for the rest (single-edge
-    contours, cusps, tiny teardrops).  Both paths must produce identical batches; B200MSDF_HOST_FLAT=0 disables the fast one."""
+    """libmsdfgen_b200_host prepares a batch straight on the flat arrays (host/flat_prep.h: no Shape objects; no allocation either
+    for glyphs whose geometry stays as it is).  B200MSDF_HOST_FLAT=0 sends every glyph through the msdfgen-compatible Shape objects
+    (Shape::normalize, edgeColoring*) instead; both entry paths must produce identical batches."""
     import os
     from util import fuzz_shape
     from msdfgen_b200.flat import FlatShapes
