@@ -306,10 +306,10 @@ inline void interpolate(T *output, const BitmapConstSection<T, N> &bitmap, Point
 }
 
 // ---- fill rule (core/Scanline.h:9-14) ---------------------------------------------------------------------------------------
-/// Fill rule dictates how intersection total is interpreted during rasterization.
+/// How the winding total along a scanline decides inside / outside.
 enum FillRule {
     FILL_NONZERO,
-    FILL_ODD, // "even-odd"
+    FILL_ODD,           // even-odd
     FILL_POSITIVE,
     FILL_NEGATIVE
 };
@@ -525,16 +525,15 @@ void msdfFastEdgeErrorCorrection(const BitmapSection<float, 4> &sdf, const Proje
 void msdfFastEdgeErrorCorrection(const BitmapSection<float, 3> &sdf, Range pxRange, double minDeviationRatio = ErrorCorrectionConfig::defaultMinDeviationRatio);
 void msdfFastEdgeErrorCorrection(const BitmapSection<float, 4> &sdf, Range pxRange, double minDeviationRatio = ErrorCorrectionConfig::defaultMinDeviationRatio);
 
-// ---- B200 additions: atlas-sized batches and device control ------------------------------------------------------------------
 // ---- scanline pass (core/Scanline.h:9-14, core/rasterization.h) -----------------------------------------------------
 
-/// Rasterizes the shape into a monochrome bitmap.
+/// 1 inside, 0 outside, per texel centre (scanline pass on the device).
 void rasterize(BitmapSection<float, 1> output, const Shape &shape, const Projection &projection, FillRule fillRule = FILL_NONZERO);
-/// Fixes the sign of the input signed distance field, so that it matches the shape's rasterized fill.
+/// Flips texels whose side of sdfZeroValue disagrees with the scanline fill of the shape (scanline pass on the device).
 void distanceSignCorrection(BitmapSection<float, 1> sdf, const Shape &shape, const Projection &projection, float sdfZeroValue = .5f, FillRule fillRule = FILL_NONZERO);
 void distanceSignCorrection(BitmapSection<float, 3> sdf, const Shape &shape, const Projection &projection, float sdfZeroValue = .5f, FillRule fillRule = FILL_NONZERO);
 void distanceSignCorrection(BitmapSection<float, 4> sdf, const Shape &shape, const Projection &projection, float sdfZeroValue = .5f, FillRule fillRule = FILL_NONZERO);
-// Old versions of the function API's kept for backwards compatibility
+// overloads of older msdfgen releases
 void rasterize(const BitmapSection<float, 1> &output, const Shape &shape, const Vector2 &scale, const Vector2 &translate, FillRule fillRule = FILL_NONZERO);
 void distanceSignCorrection(BitmapSection<float, 1> sdf, const Shape &shape, const Projection &projection, FillRule fillRule);
 void distanceSignCorrection(BitmapSection<float, 3> sdf, const Shape &shape, const Projection &projection, FillRule fillRule);
@@ -545,29 +544,30 @@ void distanceSignCorrection(const BitmapSection<float, 4> &sdf, const Shape &sha
 
 // ---- preview rendering (core/render-sdf.h) --------------------------------------------------------------------------------
 
-/// Reconstructs the shape's appearance into output from the distance field sdf.
+/// Samples the distance field at the output's resolution and thresholds it (optionally with a soft edge of sdfPxRange).
 void renderSDF(const BitmapSection<float, 1> &output, const BitmapConstSection<float, 1> &sdf, Range sdfPxRange = 0, float sdThreshold = .5f);
 void renderSDF(const BitmapSection<float, 3> &output, const BitmapConstSection<float, 1> &sdf, Range sdfPxRange = 0, float sdThreshold = .5f);
 void renderSDF(const BitmapSection<float, 1> &output, const BitmapConstSection<float, 3> &sdf, Range sdfPxRange = 0, float sdThreshold = .5f);
 void renderSDF(const BitmapSection<float, 3> &output, const BitmapConstSection<float, 3> &sdf, Range sdfPxRange = 0, float sdThreshold = .5f);
 void renderSDF(const BitmapSection<float, 1> &output, const BitmapConstSection<float, 4> &sdf, Range sdfPxRange = 0, float sdThreshold = .5f);
 void renderSDF(const BitmapSection<float, 4> &output, const BitmapConstSection<float, 4> &sdf, Range sdfPxRange = 0, float sdThreshold = .5f);
-/// Snaps the values of the floating-point bitmaps into one of the 256 values representable in a standard 8-bit bitmap.
+/// Rounds every value to what it would be after a trip through an 8-bit texture.
 void simulate8bit(const BitmapSection<float, 1> &bitmap);
 void simulate8bit(const BitmapSection<float, 3> &bitmap);
 void simulate8bit(const BitmapSection<float, 4> &bitmap);
 
 // ---- error estimation (core/sdf-error-estimation.h:19-26): evaluated on the device (sdf_error.cuh) ---------------------------------
 
-/// Estimates the portion of the area that will be filled incorrectly when rendering using the SDF.
+/// Fraction of the area whose fill, reconstructed from the SDF, differs from the shape's (scanlinesPerRow scanlines per texel row).
 double estimateSDFError(const BitmapConstSection<float, 1> &sdf, const Shape &shape, const Projection &projection, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
 double estimateSDFError(const BitmapConstSection<float, 3> &sdf, const Shape &shape, const Projection &projection, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
 double estimateSDFError(const BitmapConstSection<float, 4> &sdf, const Shape &shape, const Projection &projection, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
-// Old version of the function API's kept for backwards compatibility
+// overloads of older msdfgen releases
 double estimateSDFError(const BitmapConstSection<float, 1> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
 double estimateSDFError(const BitmapConstSection<float, 3> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
 double estimateSDFError(const BitmapConstSection<float, 4> &sdf, const Shape &shape, const Vector2 &scale, const Vector2 &translate, int scanlinesPerRow, FillRule fillRule = FILL_NONZERO);
 
+// ---- B200 additions: atlas-sized batches and device control ------------------------------------------------------------------
 namespace b200 {
 
 /// Selects the CUDA device used by the calling thread's generator context (default 0).
