@@ -536,6 +536,14 @@ int launch_k1_mode(b200msdf_ctx *ctx, KernelParams &P, int scratch) {
         int grid = 1;
         const size_t subListBytes = (size_t) (CTA_THREADS/32)*SUB_CAP*sizeof(int);      // the warps' sub-lists (dynamic shared memory)
         if ((rc = grid_for(ctx, k1_big_blocks<MODE, OVERLAP>, b->nBlocks, subListBytes, CTA_THREADS, &grid))) return rc;
+        if (OVERLAP && b->maxBigContours > B200_LOCAL_CONTOURS) {
+            // the parked per-contour state below grows with the contour count of the largest shape, not with the work: keep it
+            // under 8 GiB by launching fewer CTAs (blocks are pulled from a counter, so any grid size covers them)
+            const size_t perCta = (size_t) CTA_THREADS*(size_t) b->maxBigContours*(ModeTraits<MODE>::NOUT*sizeof(double)+1);
+            const size_t cap = size_t(8)<<30;
+            if ((size_t) grid*perCta > cap)
+                grid = cap/perCta > 1 ? (int) (cap/perCta) : 1;
+        }
         P.blocks = b->blocks.as<TileDesc>();
         P.nBlocks = b->nBlocks;
         P.listStride = ((size_t) b->maxBigSegs+3)&~size_t(3);
