@@ -296,13 +296,16 @@ __device__ inline void prepare_record(const RawShapes &rs, const GlyphDesc &g, u
                 if (fabs(bn) < 1e6)
                     flags |= SEG_CUBIC_NORMED;
             }
-            // Cusps: control point on an end point, or collinear and doubling back.  The tangent vanishes at a parameter t* in
-            // [0,1] that is itself a root of the foot-point cubic, and what the reference returns for texels nearest to the
-            // cusp hinges on the last bits of that root (is it inside (0,1)? which sign has cross(~0, q)?).  The polished roots of
-            // the fast path are accurate but not bit-faithful, so these segments take the literal closed form, which follows
-            // the reference wherever its own outcome is not rounding noise.
-            d2 pq = P2-P1;
-            if (is_zero(ab) || is_zero(pq) || (cross(ab, pq) == 0 && dot(ab, pq) < 0))
+            // Cusps: control point on an end point, or collinear and doubling back — exactly or within rounding (the same shape
+            // after a scale or a rotation).  The tangent ab + t br (all but) vanishes at a parameter t* in [0,1] that is itself a
+            // root of the foot-point cubic, and what the reference returns for texels nearest to the cusp hinges on the last bits
+            // of that root (is it inside (0,1)? which sign has cross(~0, q)?).  The polished roots of the fast path are accurate
+            // but not bit-faithful, so these segments take the literal closed form, which follows the reference wherever its own
+            // outcome is not rounding noise.  Criterion: the shortest tangent over [0,1] is below 1e-4 of the tangents' scale
+            // (ordinary outlines are nowhere near; a false positive only costs the slower solver).
+            const double tq = a != 0 ? fmin(fmax(-dot(ab, br)/a, 0.0), 1.0) : 0.0;
+            const d2 vq = ab+tq*br;
+            if (dot(vq, vq) <= 1e-8*(dot(ab, ab)+a))
                 flags |= SEG_EXACT_ROOTS;
         } else {
             d2 as = (P3-P2)-(P2-P1)-br;

@@ -45,9 +45,13 @@ struct __align__(16) FRec {
 #define FREC_CUBIC 256
 
 __device__ __forceinline__ float sqrt_approx(float x) {
+#ifdef B200_HOST_SHIM
+    return b200_shim_sqrt_approx(x);        // tests/devcore: the host stand-in, with a selectable error of the instruction's size
+#else
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#endif
 }
 
 // float not below |x| (x finite double): round to nearest, then one step up
@@ -100,6 +104,20 @@ struct FilterFrame {
     float slack;        // 2^-16 M + 2^-44 |O|
     int nGroups;        // non-empty contours
 };
+
+// Origin of the filter's local coordinates: the centre of the glyph's texel block in shape units
+__device__ __forceinline__ d2 filter_origin(const GlyphDesc &g) {
+    return mk((g.x0+.5*g.w)/g.sx-g.tx, (g.y0+.5*g.h)/g.sy-g.ty);
+}
+
+// slack of the fp32 filter for glyph g given the extent of its control points (M of the header comment: the larger of that
+// extent and the half size of the texel block)
+__device__ __forceinline__ float filter_slack(const GlyphDesc &g, d2 O, float extent) {
+    float M = extent;
+    M = fmaxf(M, float_up((.5*g.w+1)/fabs(g.sx)));
+    M = fmaxf(M, float_up((.5*g.h+1)/fabs(g.sy)));
+    return M*1.52587890625e-5f+float_up(fmax(fabs(O.x), fabs(O.y)))*5.7e-14f+1e-37f;       // 2^-16 M + 2^-44 |O|
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // The walk is split over two kernels.  k1a_filter runs passes 1 and 2 (single precision, few registers, a loop body of a few

@@ -73,11 +73,6 @@ struct KernelParams {
 
 // ---------------------------------------------------------------------------------------------------------------------
 
-// origin of the filter's local coordinates: the centre of the glyph's texel block in shape units
-__device__ __forceinline__ d2 filter_origin(const GlyphDesc &g) {
-    return mk((g.x0+.5*g.w)/g.sx-g.tx, (g.y0+.5*g.h)/g.sy-g.ty);
-}
-
 __global__ void k0_windings(RawShapes raw, int nContours, int8_t *windings, int *counters) {
     int c = blockIdx.x*blockDim.x+threadIdx.x;
     if (c == 0) {
@@ -108,14 +103,6 @@ __global__ void k0_prepare_big(RawShapes raw, const GlyphDesc *glyphs, const int
             perp[size_t(g.recBase)+j] = q;
         }
     }
-}
-
-// slack of the fp32 filter for glyph g given the extent of its control points (distance_filter.cuh)
-__device__ __forceinline__ float filter_slack(const GlyphDesc &g, d2 O, float extent) {
-    float M = extent;
-    M = fmaxf(M, float_up((.5*g.w+1)/fabs(g.sx)));
-    M = fmaxf(M, float_up((.5*g.h+1)/fabs(g.sy)));
-    return M*1.52587890625e-5f+float_up(fmax(fabs(O.x), fabs(O.y)))*5.7e-14f+1e-37f;       // 2^-16 M + 2^-44 |O|
 }
 
 // second preparation pass of big shapes: the filter records (need the shape's extent, known after k0_prepare_big)

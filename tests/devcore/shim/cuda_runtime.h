@@ -1,0 +1,62 @@
+// cuda_runtime.h — HOST SHIM for tests/devcore only (never on the product's include path).
+//
+// Lets g++ compile the per-thread device functions of msdfgen_b200/csrc/distance_core.cuh unchanged, as ordinary C++: the CUDA
+// qualifiers vanish, the handful of intrinsics the file uses get host definitions, and "the current thread" is thread 0 of a
+// one-thread block.  Only code without warp- or block-level cooperation can be compiled this way; that is exactly the texel
+// semantics (segment kernels, root solvers, selectors, combiners), which is what the CPU test checks against the oracle.
+#pragma once
+
+#include <climits>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define __align__(n) __attribute__((aligned(n)))
+#define __shared__ static
+#define __restrict__
+
+struct double2 { double x, y; };
+struct DevcoreIdx { unsigned x, y, z; };
+static const DevcoreIdx threadIdx = { 0, 0, 0 }, blockIdx = { 0, 0, 0 };
+
+// fp32 helpers of the fast foot-point path.  The device versions are approximate (__cosf) or plain IEEE (__frcp_rn); the values
+// only seed a double-precision polish, so any implementation within a few ulp of the true function serves the same purpose.
+#define __cosf(x) cosf(x)       // (glibc declares an internal function of this name: a macro, not a definition)
+static inline float __frcp_rn(float x) { return 1.0f/x; }
+using std::isfinite;
+
+template <typename T> static inline T atomicAdd(T *p, T v) { T old = *p; *p += v; return old; }
+
+// ---- the fp32 filter (distance_filter.cuh) -----------------------------------------------------------------------------------------
+#define B200_HOST_SHIM 1
+struct float4 { float x, y, z, w; };
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+static inline float __saturatef(float x) { return x >= 0.f ? (x <= 1.f ? x : 1.f) : 0.f; }       // NaN -> 0 like the instruction
+static inline int __float_as_int(float x) { int r; memcpy(&r, &x, 4); return r; }
+static inline unsigned __float_as_uint(float x) { unsigned r; memcpy(&r, &x, 4); return r; }
+static inline float __int_as_float(int x) { float r; memcpy(&r, &x, 4); return r; }
+static inline float __uint_as_float(unsigned x) { float r; memcpy(&r, &x, 4); return r; }
+static inline int __ffs(unsigned x) { return __builtin_ffs((int) x); }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+// round-up conversion: the nearest float, stepped up if it fell below
+static inline float __double2float_ru(double x) {
+    float f = (float) x;
+    return (double) f < x ? nextafterf(f, INFINITY) : f;
+}
+// A "warp" is one lane here, so a warp-wide OR is the lane's own value: exact_texel walks the union of its lanes' survivors and
+// every lane acts only on its own bits, hence a lane's result does not depend on its neighbours.
+static inline unsigned __reduce_or_sync(unsigned, unsigned x) { return x; }
+// sqrt.approx.ftz.f32 has a maximum relative error of 2^-23 (PTX ISA); the stand-in is the correctly rounded root pushed by
+// b200_shim_sqrt_bias * 2^-22 in either direction, so the tests cover twice the instruction's error on both sides.
+extern int b200_shim_sqrt_bias;
+static inline float b200_shim_sqrt_approx(float x) {
+    const float r = sqrtf(x);
+    return b200_shim_sqrt_bias ? r*(1.f+b200_shim_sqrt_bias*2.384185791015625e-7f) : r;
+}
