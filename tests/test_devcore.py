@@ -270,3 +270,81 @@ def test_cusps_under_affine_maps(devcore, ref):
                 values += d.size
     assert different <= 1e-4 * values, (different, values)
     print(f"[devcore] cusps under affine maps: {different} of {values} values differ (libm-dependent texels of the reference)")
+
+
+# ---- random shape soup -----------------------------------------------------------------------------------------------------------
+
+def _soup(rng, kind):
+    """1-4 closed contours of 2-8 random edges (self-intersecting at will).  kind: plain | grid (integer coordinates: exact ties)
+    | mixed (vertex clouds of size 1e-6, 1 and 1e3 in one shape) | repeated (an edge listed twice) | sliver (control points on or
+    within 1e-12 .. 1e-3 of the chord's line, also beyond its ends: near-straight edges, doubled-back edges, zero-area contours)."""
+    rows, orders, cbegin = [], [], [0]
+    for _ in range(rng.integers(1, 5)):
+        n = rng.integers(2, 9)
+        if kind == "grid":
+            v = rng.integers(-8, 9, size=(n, 2)).astype(float)
+        elif kind == "mixed":
+            v = rng.normal(size=(n, 2)) * rng.choice([1e-6, 1.0, 1e3], size=(n, 1))
+        else:
+            v = rng.normal(size=(n, 2)) * 4
+        for i in range(n):
+            a, b = v[i], v[(i + 1) % n]
+            order = int(rng.integers(1, 4))
+            if kind == "sliver":
+                t = rng.uniform(-0.3, 1.3, 2)
+                eps = rng.choice([0, 1e-12, 1e-7, 1e-3])
+                normal = np.array([a[1] - b[1], b[0] - a[0]])
+                c1, c2 = a + (b - a) * t[0] + normal * eps * rng.normal(), a + (b - a) * t[1] + normal * eps * rng.normal()
+            elif kind == "grid":
+                c1, c2 = rng.integers(-8, 9, 2).astype(float), rng.integers(-8, 9, 2).astype(float)
+            else:
+                c1, c2 = (a + b) / 2 + rng.normal(size=2) * 2, (a + b) / 2 + rng.normal(size=2) * 2
+            if kind == "repeated" and i and rng.random() < 0.3:
+                rows.append(rows[-1])
+                orders.append(orders[-1])
+                continue
+            row = np.zeros(8)
+            row[:2 * (order + 1)] = np.concatenate([a, b] if order == 1 else [a, c1, b] if order == 2 else [a, c1, c2, b])
+            rows.append(row)
+            orders.append(order)
+        cbegin.append(len(orders))
+    colors = np.array([(6, 5, 3)[i % 3] for i in range(len(orders))], np.uint8)
+    return FlatShapes.single(np.array(cbegin, np.uint32), np.array(rows), np.array(orders, np.uint8), colors)
+
+
+def _soup_run(lib, oracle, kind, seed, count):
+    rng = np.random.default_rng(seed)
+    values = different = 0
+    for it in range(count):
+        g = _soup(rng, kind)
+        if not np.all(np.ptp(_control_points(g), 0) > 0):
+            continue
+        xf = _frame(g, 24, 24)
+        pts = _texels(xf, 24, 24, rng, extra=100)
+        for mode, overlap in ((1, True), (2, False), (3, True), (4, False), (3, False), (4, True)):
+            want = oracle.distance(mode, overlap, g.cbegin, g.points, g.orders, g.colors, pts)
+            for policy in (FAST_GUARDED, FOLDED):
+                got, _ = _filtered(lib, mode, overlap, policy, it % 3 - 1, g, xf, 24, 24, pts)
+                d = (_texel_bits(got, xf) != _texel_bits(want, xf)) & ~(np.isnan(got) & np.isnan(want))
+                different += int(d.sum())
+                values += d.size
+    return values, different
+
+
+@pytest.mark.parametrize("kind", ["plain", "mixed", "repeated"])
+def test_random_shape_soup(devcore, ref, kind):
+    values, different = _soup_run(devcore, ref, kind, seed=7, count=120)
+    assert different == 0, (different, values)
+
+
+def test_random_slivers_and_lattice_soup_known_limit(devcore, ref):
+    """Two constructions reach what the fast root path does not guard: a NEAR-TIE BETWEEN TWO DIFFERENT EDGES one of whose distances
+    comes from a polished root.  An edge retraced backwards by its neighbour (zero-area sliver contour) and curve soup on an
+    integer lattice put whole regions of texels at equal distance from two edges of opposite orientation; the reference's winner
+    is decided in the last bit of its closed-form root, the fast path's distance can differ in that bit, and the other edge's sign
+    wins (every per-segment distance still agrees to 1e-9 relative — see DESIGN.md section 2).  quad_root's guard band only covers
+    ties between roots of the SAME segment.  Measured here and bounded, so that a change of the rate is noticed."""
+    values_s, different_s = _soup_run(devcore, ref, "sliver", seed=7, count=200)
+    values_g, different_g = _soup_run(devcore, ref, "grid", seed=7, count=200)
+    print(f"[devcore] unguarded cross-edge near-ties: slivers {different_s} of {values_s} values, lattice soup {different_g} of {values_g}")
+    assert different_s <= 2e-3 * values_s and different_g <= 2e-4 * values_g
