@@ -1,0 +1,150 @@
+"""TrueType glyph ingest (msdfgen_b200/host/font_ingest.cpp): the FreeType-free counterpart of msdfgen's
+ext/import-font.  The image ships one TrueType font (an icon font inside the CUDA toolkit's HTML documentation: 676 outlines of
+up to 39 contours and 364 segments, abutting contours, shared edges) and Pillow bundles a FreeType of its own — so the ingest is
+checked against FreeType's rendering of the same glyphs, and the real outlines then go through the host-compiled texel path
+(tests/devcore) against the compiled reference.  tests/test_zz_real_font.py is the GPU leg."""
+import glob
+
+import numpy as np
+import pytest
+
+from msdfgen_b200 import prep
+from msdfgen_b200.flat import FlatShapes
+
+CANDIDATES = sorted(glob.glob("/usr/local/cuda*/compute-sanitizer/docs/_static/css/fonts/fontawesome-webfont.ttf") +
+                    glob.glob("/opt/nvidia/nsight-compute/*/docs/_static/css/fonts/fontawesome-webfont.ttf"))
+
+
+@pytest.fixture(scope="module")
+def font():
+    if not CANDIDATES:
+        pytest.skip("no TrueType font in this image")
+    from msdfgen_b200.font import Font
+    return Font(CANDIDATES[0])
+
+
+def test_tables_and_character_map(font):
+    assert font.n_glyphs == 707 and font.units_per_em == 1792
+    assert (font.ascender, font.descender, font.line_height) == (1536, -256, 1792)
+    gi = font.glyph_indices(np.arange(0xf000, 0xf2e1))
+    assert (gi > 0).sum() == 679 and gi[0] == 13 and len(set(gi[gi > 0])) == 679
+    assert font.glyph_indices([0x41, 0x10ffff, 0x20]).tolist()[:2] == [0, 0]
+
+
+def test_flat_batch_is_well_formed(font):
+    shapes, advances, loaded = font.load_glyphs(np.arange(font.n_glyphs), "none")
+    assert loaded.all() and shapes.n_glyphs == 707
+    assert set(np.unique(shapes.orders)) == {1, 2}                      # TrueType: lines and quadratics
+    assert prep.validate(shapes)                                        # every contour closed, edge to edge
+    assert (advances > 0).sum() > 600 and advances.max() <= 2 * 1792
+    # no zero-length edges, no empty contours; coordinates are integers (implied points use FreeType's integer halving)
+    assert (np.diff(shapes.cbegin) > 0).all()
+    ends = np.array([shapes.points[i, 2 * o:2 * o + 2] for i, o in enumerate(shapes.orders)])
+    assert (np.abs(ends - shapes.points[:, :2]).sum(1) > 0).all()
+    assert np.array_equal(shapes.points, np.round(shapes.points))
+    # scalings: every point is `scale*vector.x`; the factory's lowering of degenerate quadratics runs on the SCALED points (as in
+    # the reference), so a control point that is collinear in integers may stop being so after scaling — orders may differ
+    em, _, _ = font.load_glyphs([40, 361], "em")
+    raw, _, _ = font.load_glyphs([40, 361], "none")
+    assert np.array_equal(em.cbegin, raw.cbegin) and np.array_equal(em.points[:, :2], (1.0 / 1792) * raw.points[:, :2])
+    assert (em.orders >= raw.orders).all()
+    # bad glyph indices fail softly
+    bad, _, ok = font.load_glyphs([5, 100000], "em")
+    assert ok.tolist() == [True, False] and bad.n_glyphs == 2
+
+
+def test_outlines_match_freetype_rendering(font, port):
+    """Inside / outside of the ingested outline (the oracle's scanline rasteriser, non-zero rule) against FreeType's anti-aliased
+    rendering of the same glyph in Pillow, on pixels FreeType renders clearly black or white.  FreeType hints the outline (stems
+    snap to the pixel grid), so a fraction of a percent along edges may differ; a missing contour, a wrong implied point or a
+    wrong start rule would flip whole regions."""
+    ImageFont = pytest.importorskip("PIL.ImageFont")
+    size = 96
+    pil = ImageFont.truetype(CANDIDATES[0], size, layout_engine=ImageFont.Layout.BASIC)
+    ascent, _ = pil.getmetrics()
+    shapes, _, _ = font.load_glyphs(np.arange(font.n_glyphs), "none")
+    scale = size / font.units_per_em
+    cps = np.arange(0xf000, 0xf2e1)
+    compared = different = 0
+    for cp, g in list(zip(cps, font.glyph_indices(cps)))[::5]:
+        cb, pts, od, cl, _ = shapes.glyph(int(g))
+        mask = pil.getmask(chr(int(cp)), mode="L")
+        w, h = mask.size
+        if g == 0 or len(od) == 0 or w == 0 or h == 0:
+            continue
+        left, top = pil.getbbox(chr(int(cp)))[:2]
+        xf = (scale, scale, -left / scale, -(ascent - top - h) / scale, -1 / scale, 1 / scale)
+        inside = port.rasterize(cb, pts, od, xf, w, h, 0).reshape(h, w)[::-1] > 0.5
+        coverage = np.asarray(mask, np.uint8).reshape(h, w)
+        clear = (coverage > 200) | (coverage < 55)
+        different += int(((inside != (coverage > 127)) & clear).sum())
+        compared += int(clear.sum())
+    assert compared > 500000 and different <= 0.005 * compared, (different, compared)
+
+
+from test_devcore import devcore  # noqa: E402,F401  (the fixture that builds tests/devcore)
+
+
+def test_real_glyphs_through_the_texel_path(font, ref, devcore):
+    """Normalised, coloured real outlines through k1a's filter + k1b's walk (the big-shape form for glyphs above 96 segments),
+    compiled for the host: every float equals the reference's, including glyph 361, whose two abutting contours share three
+    quadratic edges traversed in opposite directions (prepare_record's twin rule sends those to the literal solver)."""
+    from test_devcore import _filtered, _frame, _texels, _texel_bits, FAST_GUARDED, FOLDED
+    lib = devcore
+    raw, _, _ = font.load_glyphs(np.arange(font.n_glyphs), "em")
+    shapes = prep.prepare(raw)
+    rng = np.random.default_rng(3)
+    values = 0
+    for g in sorted(set(range(0, font.n_glyphs, 9)) | {361}):
+        cb, pts, od, cl, _ = shapes.glyph(g)
+        if len(od) == 0:
+            continue
+        s = FlatShapes.single(cb, pts, od, cl)
+        w = h = 32 if g % 2 else 48
+        xf = _frame(s, w, h)
+        texels = _texels(xf, w, h, rng)
+        for mode, overlap in ((3, True), (4, True), (1, True), (3, False), (2, False)):
+            want = ref.distance(mode, overlap, s.cbegin, s.points, s.orders, s.colors, texels)
+            got, _ = _filtered(lib, mode, overlap, FOLDED if len(od) > 96 else FAST_GUARDED, g % 3 - 1, s, xf, w, h, texels)
+            assert np.array_equal(_texel_bits(got, xf), _texel_bits(want, xf)), (g, len(od), mode, overlap)
+            values += got.size
+    print(f"[font] {values} values of real glyphs identical")
+
+
+def test_shape_interface_equals_flat_ingest(font):
+    """msdfgen's calls (initializeFreetype, loadFont, loadGlyph by code point, getFontMetrics) from a C++ caller give the same
+    edges as the batch ingest, and normalize + edgeColoringSimple on the Shape equal prep.prepare on the flat glyph."""
+    import ctypes as C
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src, out = os.path.join(root, "tests", "dropin", "font_caller.cpp"), os.path.join(root, "tests", "dropin", "_build")
+    host = os.path.join(root, "msdfgen_b200")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libfont_caller.so")
+    deps = [src, os.path.join(host, "libmsdfgen_b200_host.so"), os.path.join(host, "host", "import-font.h")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.run([cxx, "-O2", "-ffp-contract=off", "-std=c++11", "-fPIC", "-shared", f"-I{host}/host", "-o", lib, src, f"-L{host}",
+                        "-lmsdfgen_b200_host", "-lmsdfgen_b200", f"-Wl,-rpath,{host}"], check=True, capture_output=True)
+    caller = C.CDLL(lib)
+    for cp in (0xf000, 0xf02a, 0xf013, 0xf1ea):
+        g = int(font.glyph_indices([cp])[0])
+        for scaling, name in ((0, "none"), (1, "em"), (2, "legacy")):
+            flat, adv, _ = font.load_glyphs([g], name)
+            for prepare in (0, 1):
+                want = prep.prepare(flat) if prepare else flat
+                cap = 4 * len(flat.orders) + 16
+                cb, pts = np.zeros(cap + 1, np.uint32), np.zeros((cap, 8))
+                od, cl = np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)
+                advance, metrics = C.c_double(0), np.zeros(6)
+                nc = caller.font_caller_glyph(CANDIDATES[0].encode(), C.c_uint(cp), C.c_int(scaling), C.c_int(prepare), C.c_int(cap), C.c_int(cap),
+                                              cb.ctypes.data_as(C.POINTER(C.c_uint32)), pts.ctypes.data_as(C.POINTER(C.c_double)),
+                                              od.ctypes.data_as(C.POINTER(C.c_uint8)), cl.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(advance),
+                                              metrics.ctypes.data_as(C.POINTER(C.c_double)))
+                assert nc == want.n_contours, (hex(cp), name, prepare, nc)
+                ns = int(cb[nc])
+                assert np.array_equal(cb[:nc + 1], want.cbegin) and np.array_equal(od[:ns], want.orders) and np.array_equal(cl[:ns], want.colors)
+                assert np.array_equal(pts[:ns].view(np.uint64), want.points.view(np.uint64))
+                assert advance.value == adv[0]
+                assert np.allclose(metrics, np.array([1792, 1536, -256, 1792, 0, 0]) * font.scale(name), rtol=0, atol=0)
