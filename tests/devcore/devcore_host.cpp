@@ -118,7 +118,7 @@ int runFiltered(const Prepared &pr, const GlyphDesc &g, const uint32_t *cbegin, 
         const unsigned lane = (unsigned) i&31u;         // the words of a unit's 32 texels are interleaved: use every lane slot
         double *dist = out+(size_t) i*NOUT;
         guard_flag() = 0;
-        if (policy == 3)
+        if (policy == 3 || policy == 4)
             shape_distance_list_filtered<MODE, OVERLAP, SeqIter>(pr.recs.data(), frecs.data(), nRec, SeqIter(), O, slack, p, fold, dist);
         else {
             std::fill(block.begin(), block.end(), 0xdeadbeefu);
@@ -143,7 +143,7 @@ int runFiltered(const Prepared &pr, const GlyphDesc &g, const uint32_t *cbegin, 
         if (guard_flag()) {
             ++guardHits;
             guard_flag() = 0;
-            if (policy != 0)
+            if (policy != 0 && policy != 4)
                 shape_distance<MODE, OVERLAP, true>(pr.recs.data(), nRec, p, store, dist);
         }
     }
@@ -156,7 +156,8 @@ int runFiltered(const Prepared &pr, const GlyphDesc &g, const uint32_t *cbegin, 
 
 extern "C" {
 
-/// The filtered path (k1a_filter + k1b_exact; policy 3: the big-shape kernel's single-pass form) at nPts points inside the w x h
+/// The filtered path (k1a_filter + k1b_exact; policy 3: the big-shape kernel's single-pass form, 4: the same without the literal
+/// redo of texels that hit the guard band — what k1_big_blocks does today) at nPts points inside the w x h
 /// texel block of the projection xf = (sx, sy, tx, ty).  sqrtBias: error of the stand-in for sqrt.approx in units of 2^-22
 /// (-1, 0, +1).  Otherwise as devcore_distance; survivorsPerTexel receives the mean number of exact edge evaluations per texel.
 int devcore_distance_filtered(int mode, int overlap, int policy, int sqrtBias, int nContours, const uint32_t *cbegin, const double *points,

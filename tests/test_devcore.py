@@ -28,6 +28,7 @@ OUT = os.path.join(ROOT, "tests", "devcore", "_build")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 CHANNELS = {1: 1, 2: 1, 3: 3, 4: 4}
 FAST_GUARDED, LITERAL, FOLDED = 1, 2, 3
+FOLDED_UNGUARDED = 4        # the big-shape kernel as it runs today: texels that hit the guard band are NOT redone with the literal solver
 
 
 @pytest.fixture(scope="module")

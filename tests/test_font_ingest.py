@@ -89,7 +89,7 @@ def test_real_glyphs_through_the_texel_path(font, ref, devcore):
     """Normalised, coloured real outlines through k1a's filter + k1b's walk (the big-shape form for glyphs above 96 segments),
     compiled for the host: every float equals the reference's, including glyph 361, whose two abutting contours share three
     quadratic edges traversed in opposite directions (prepare_record's twin rule sends those to the literal solver)."""
-    from test_devcore import _filtered, _frame, _texels, _texel_bits, FAST_GUARDED, FOLDED
+    from test_devcore import _filtered, _frame, _texels, _texel_bits, FAST_GUARDED, FOLDED_UNGUARDED
     lib = devcore
     raw, _, _ = font.load_glyphs(np.arange(font.n_glyphs), "em")
     shapes = prep.prepare(raw)
@@ -105,7 +105,7 @@ def test_real_glyphs_through_the_texel_path(font, ref, devcore):
         texels = _texels(xf, w, h, rng)
         for mode, overlap in ((3, True), (4, True), (1, True), (3, False), (2, False)):
             want = ref.distance(mode, overlap, s.cbegin, s.points, s.orders, s.colors, texels)
-            got, _ = _filtered(lib, mode, overlap, FOLDED if len(od) > 96 else FAST_GUARDED, g % 3 - 1, s, xf, w, h, texels)
+            got, _ = _filtered(lib, mode, overlap, FOLDED_UNGUARDED if len(od) > 96 else FAST_GUARDED, g % 3 - 1, s, xf, w, h, texels)
             assert np.array_equal(_texel_bits(got, xf), _texel_bits(want, xf)), (g, len(od), mode, overlap)
             values += got.size
     print(f"[font] {values} values of real glyphs identical")
