@@ -21,6 +21,21 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.EXPORTS) == declared
 
 
+def test_host_library_exports_every_declared_symbol():
+    """include/msdfgen_b200_host.h (batch preparation, font ingest) against libmsdfgen_b200_host.so, and the header compiles as C."""
+    import subprocess
+    from msdfgen_b200 import prep
+    path = os.path.join(ROOT, "include", "msdfgen_b200_host.h")
+    declared = sorted(set(re.findall(r"\b(b200host_[a-z_0-9]+)\s*\(", open(path).read())))
+    assert len(declared) >= 14
+    lib = prep.host_lib()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    exported = subprocess.run(["nm", "-D", "--defined-only", prep.HOST_LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert sorted(set(re.findall(r"\b(b200host_[a-z_0-9]+)\b", exported))) == declared
+    subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-x", "c", path], check=True, capture_output=True)
+
+
 def test_version_and_default_config():
     lib = _lib.load()
     assert lib.b200msdf_version() == 101
