@@ -16,6 +16,7 @@
 using namespace b200;
 
 int b200_shim_sqrt_bias = 0;
+int b200_shim_cos_bias = 0;
 
 namespace {
 
@@ -158,8 +159,8 @@ extern "C" {
 
 /// The filtered path (k1a_filter + k1b_exact; policy 3: the big-shape kernel's single-pass form, 4: the same without the literal
 /// redo of texels that hit the guard band — what k1_big_blocks does today) at nPts points inside the w x h
-/// texel block of the projection xf = (sx, sy, tx, ty).  sqrtBias: error of the stand-in for sqrt.approx in units of 2^-22
-/// (-1, 0, +1).  Otherwise as devcore_distance; survivorsPerTexel receives the mean number of exact edge evaluations per texel.
+/// texel block of the projection xf = (sx, sy, tx, ty).  sqrtBias: error of the stand-ins for sqrt.approx (in units of 2^-22 relative) and __cosf (in units
+/// of 1e-6 absolute): -1, 0, +1.  Otherwise as devcore_distance; survivorsPerTexel receives the mean number of exact edge evaluations per texel.
 int devcore_distance_filtered(int mode, int overlap, int policy, int sqrtBias, int nContours, const uint32_t *cbegin, const double *points,
                               const uint8_t *orders, const uint8_t *colors, const double *xf, int w, int h, int nPts, const double *pts, double *out,
                               double *survivorsPerTexel) {
@@ -172,6 +173,7 @@ int devcore_distance_filtered(int mode, int overlap, int policy, int sqrtBias, i
     g.nonEmptyContours = pr.nonEmpty;
     g.recBase = -1;
     b200_shim_sqrt_bias = sqrtBias;
+    b200_shim_cos_bias = sqrtBias;          // one knob: both approximate instructions err the same way, then the other way
     int rc = -1;
     switch (mode*2+(overlap != 0)) {
         case 2: rc = runFiltered<1, false>(pr, g, cbegin, policy, nPts, pts, out, survivorsPerTexel); break;
@@ -183,7 +185,7 @@ int devcore_distance_filtered(int mode, int overlap, int policy, int sqrtBias, i
         case 8: rc = runFiltered<4, false>(pr, g, cbegin, policy, nPts, pts, out, survivorsPerTexel); break;
         case 9: rc = runFiltered<4, true>(pr, g, cbegin, policy, nPts, pts, out, survivorsPerTexel); break;
     }
-    b200_shim_sqrt_bias = 0;
+    b200_shim_sqrt_bias = b200_shim_cos_bias = 0;
     return rc;
 }
 
