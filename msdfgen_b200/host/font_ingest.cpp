@@ -8,6 +8,7 @@
 #include "import-font.h"
 #include "flat_geom.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -41,6 +42,7 @@ public:
     bool parse();
     unsigned glyphIndex(unicode_t unicode) const;
     int advance(unsigned glyph) const;
+    int leftSideBearing(unsigned glyph) const;
     bool outline(unsigned glyph, std::vector<IPoint> &points, std::vector<int> &contourEnds, int depth = 0) const;
     bool kerning(unsigned left, unsigned right, int &value) const;
     // the edges of a glyph as msdfgen's FreeType callbacks build them; cbegin gets one entry per contour END (appended)
@@ -167,6 +169,14 @@ int FontHandle::advance(unsigned glyph) const {
         return 0;
     const unsigned i = glyph < (unsigned) numHMetrics ? glyph : (unsigned) numHMetrics-1;
     return (int) u16(hmtx.offset+4*(size_t) i);
+}
+
+int FontHandle::leftSideBearing(unsigned glyph) const {
+    if (numHMetrics <= 0)
+        return 0;
+    if (glyph < (unsigned) numHMetrics)
+        return i16(hmtx.offset+4*(size_t) glyph+2);
+    return i16(hmtx.offset+4*(size_t) numHMetrics+2*(size_t) (glyph-(unsigned) numHMetrics));
 }
 
 bool FontHandle::glyphRange(unsigned glyph, size_t &begin, size_t &end) const {
@@ -303,10 +313,11 @@ bool FontHandle::outline(unsigned glyph, std::vector<IPoint> &points, std::vecto
         if (flags&2) {
             dx = arg1;
             dy = arg2;
-            if (transformed && (flags&0x800)) {             // SCALED_COMPONENT_OFFSET
-                const long ox = dx, oy = dy;
-                dx = mulFix(ox, xx)+mulFix(oy, xy);
-                dy = mulFix(ox, yx)+mulFix(oy, yy);
+            if (transformed && (flags&0x800)) {
+                // SCALED_COMPONENT_OFFSET (Apple's convention): the offset is stretched by the lengths of the transformed unit
+                // vectors (FreeType computes them with its integer hypot; a correctly rounded one stands in here)
+                dx = mulFix(dx, std::lround(std::hypot((double) xx, (double) xy)));
+                dy = mulFix(dy, std::lround(std::hypot((double) yy, (double) yx)));
             }
         } else {
             // point matching: parent point arg1 and component point arg2 coincide
@@ -416,6 +427,14 @@ bool FontHandle::decompose(unsigned glyph, double scale, std::vector<flat::Seg> 
     std::vector<int> ends;
     if (!outline(glyph, points, ends))
         return false;
+    // The glyph's origin is where its left side bearing says it is: FreeType moves every TrueType outline by the difference
+    // between the xMin of the glyph's header and the lsb of `hmtx` (zero in a well-formed font).
+    size_t g0, g1;
+    if (glyphRange(glyph, g0, g1) && g1-g0 >= 10) {
+        const long shift = (long) i16(g0+2)-leftSideBearing(glyph);
+        for (size_t i = 0; shift && i < points.size(); ++i)
+            points[i].x -= shift;
+    }
     EdgeSink sink = { scale, segs, cbegin, segs.size(), false, Point2() };
     int first = 0;
     for (size_t c = 0; c < ends.size(); ++c) {

@@ -148,3 +148,106 @@ def test_shape_interface_equals_flat_ingest(font):
                 assert np.array_equal(pts[:ns].view(np.uint64), want.points.view(np.uint64))
                 assert advance.value == adv[0]
                 assert np.allclose(metrics, np.array([1792, 1536, -256, 1792, 0, 0]) * font.scale(name), rtol=0, atol=0)
+
+
+# ---- synthetic fonts: the paths the image's font does not exercise ------------------------------------------------------------------
+
+def _against_freetype(data, chars, port, size=120):
+    """(clear pixels compared, pixels that differ) between the ingested outlines' fill and FreeType's rendering of the same bytes"""
+    import io
+    from PIL import ImageFont
+    from msdfgen_b200.font import Font
+    f = Font(data)
+    pil = ImageFont.truetype(io.BytesIO(data), size, layout_engine=ImageFont.Layout.BASIC)
+    ascent, _ = pil.getmetrics()
+    scale = size / f.units_per_em
+    compared = different = 0
+    for ch in chars:
+        g = int(f.glyph_indices([ord(ch)])[0])
+        assert g != 0
+        shapes, _, ok = f.load_glyphs([g], "none")
+        assert ok[0] and len(shapes.orders)
+        mask = pil.getmask(ch, mode="L")
+        w, h = mask.size
+        left, top = pil.getbbox(ch)[:2]
+        xf = (scale, scale, -left / scale, -(ascent - top - h) / scale, -1 / scale, 1 / scale)
+        inside = port.rasterize(shapes.cbegin, shapes.points, shapes.orders, xf, w, h, 0).reshape(h, w)[::-1] > 0.5
+        coverage = np.asarray(mask, np.uint8).reshape(h, w)
+        clear = (coverage > 215) | (coverage < 40)
+        different += int(((inside != (coverage > 127)) & clear).sum())
+        compared += int(clear.sum())
+    return compared, different
+
+
+def test_contours_that_start_on_control_points(port):
+    """FT_Outline_Decompose's start rules: first point off the curve and last point on it (start there), both off (start halfway,
+    integer halving), control points only (every on-curve point implied); plus an ordinary contour as the control."""
+    pytest.importorskip("PIL.ImageFont")
+    from ttf_builder import build, simple, ON, OFF
+    blob = [(500, 60, OFF), (900, 120, ON), (960, 500, OFF), (880, 900, OFF), (470, 950, ON), (90, 880, OFF), (55, 430, OFF), (130, 101, ON)]
+    glyphs = [simple([]),
+              simple([blob]),                                                                   # first off, last on
+              simple([blob[:-1]]),                                                              # first off, last off
+              simple([[(x, y, OFF) for x, y, _ in blob]]),                                      # control points only
+              simple([blob[1:] + blob[:1]]),                                                    # first on (control)
+              simple([[(501, 61, OFF), (901, 121, OFF), (961, 501, OFF), (101, 901, OFF), (33, 333, OFF)], blob[1:5]])]   # odd sums: halving truncates
+    data = build(glyphs, {ord("A") + i: i + 1 for i in range(5)})
+    compared, different = _against_freetype(data, "ABCDE", port)
+    assert compared > 30000 and different <= 0.004 * compared, (different, compared)
+    # the implied points themselves: integer halving towards zero, as FT_Outline_Decompose does it
+    from msdfgen_b200.font import Font
+    shapes, _, _ = Font(data).load_glyphs([5], "none")
+    starts = {tuple(p) for p in shapes.points[:, :2]}
+    assert (701.0, 91.0) in starts and (931.0, 311.0) in starts and (267.0, 197.0) in starts        # (501+901)/2, (61+121)/2, ... (33+501)/2, (333+61)/2
+    # a left side bearing that disagrees with the outline's xMin moves the outline (FreeType puts the origin where `hmtx` says)
+    moved = build(glyphs, {ord("A") + i: i + 1 for i in range(5)}, lsb=[0, 0, 100, 55, 130, 33])
+    compared, different = _against_freetype(moved, "ABCDE", port)
+    assert different <= 0.004 * compared, (different, compared)
+    a, _, _ = Font(moved).load_glyphs([1, 2], "none")
+    b, _, _ = Font(data).load_glyphs([1, 2], "none")
+    assert np.array_equal(a.points[:, 0::2][b.points[:, 0::2] != 0], (b.points[:, 0::2] - np.repeat([[55], [-45]], [5, len(a.orders) - 5], 0))[b.points[:, 0::2] != 0])
+
+
+def test_composite_glyphs(port):
+    """Components with plain offsets, a uniform scale, separate x / y scales, a 2x2 matrix (rotation + shear), nesting, and point
+    matching — assembled in 16.16 arithmetic like FreeType's loader, rendered by FreeType for comparison."""
+    pytest.importorskip("PIL.ImageFont")
+    from ttf_builder import build, simple, composite, ON, OFF
+    bar = simple([[(0, 0, ON), (0, 600, ON), (150, 600, ON), (150, 0, ON)]])
+    drop = simple([[(300, 50, ON), (100, 300, OFF), (300, 700, ON), (500, 300, OFF)]])
+    glyphs = [simple([]), bar, drop,
+              composite([{"glyph": 1, "dx": 100, "dy": 100}, {"glyph": 1, "dx": 500, "dy": 250}, {"glyph": 2, "dx": 250, "dy": 120}]),
+              composite([{"glyph": 2, "dx": 40, "dy": 30, "scale": 0.61803}, {"glyph": 2, "dx": 420, "dy": 350, "scale": 0.75}]),
+              composite([{"glyph": 2, "dx": 10, "dy": 10, "xscale": 1.5, "yscale": 0.5}, {"glyph": 1, "dx": 700, "dy": 300, "xscale": 0.4, "yscale": 1.1}]),
+              composite([{"glyph": 2, "dx": 500, "dy": 100, "matrix": (0.8, 0.5, -0.45, 0.85)}, {"glyph": 1, "dx": 50, "dy": 50, "matrix": (1.0, 0.0, 0.37, 1.0)}]),
+              composite([{"glyph": 4, "dx": 0, "dy": 0}, {"glyph": 3, "dx": 60, "dy": 40, "scale": 0.5}]),          # nested composites
+              composite([{"glyph": 1, "dx": 200, "dy": 100}, {"glyph": 2, "match": (2, 0)}])]                       # drop's point 0 on bar's point 2
+    data = build(glyphs, {ord("A") + i: i + 3 for i in range(6)})
+    compared, different = _against_freetype(data, "ABCDEF", port)
+    assert compared > 40000 and different <= 0.004 * compared, (different, compared)
+    from msdfgen_b200.font import Font
+    f = Font(data)
+    plain, _, _ = f.load_glyphs([3], "none")
+    assert plain.n_contours == 3 and len(plain.orders) == 4 + 4 + 2
+    scaled, _, _ = f.load_glyphs([4], "none")
+    # mulFix(300, round(0.61803 * 16384) * 4) + 40: the 2.14 scale widened to 16.16, products rounded to nearest
+    s = round(0.61803 * 16384) * 4
+    assert scaled.points[0, 0] == ((300 * s + 0x8000) >> 16) + 40 and scaled.points[0, 1] == ((50 * s + 0x8000) >> 16) + 30
+    matched, _, _ = f.load_glyphs([8], "none")
+    assert {(350.0, 700.0)} <= {tuple(p) for p in matched.points[:, :2]}                  # bar's point 2 (150, 600) + (200, 100)
+
+
+def test_character_maps_and_kerning():
+    from ttf_builder import build, simple, ON
+    from msdfgen_b200.font import Font
+    box = simple([[(0, 0, ON), (0, 500, ON), (500, 500, ON), (500, 0, ON)]])
+    cmap = {0x41: 1, 0x42: 2, 0x3b1: 3, 0x1f600: 4, 0x20: 5}
+    kern = {(1, 2): -80, (2, 1): 35, (3, 4): -7}
+    for cmap12 in (False, True):
+        f = Font(build([simple([]), box, box, box, box, simple([])], cmap, advances=[500, 600, 610, 620, 630, 250], kern=kern, cmap12=cmap12))
+        want = [1, 2, 3, 4 if cmap12 else 0, 5, 0]
+        assert f.glyph_indices([0x41, 0x42, 0x3b1, 0x1f600, 0x20, 0x43]).tolist() == want
+        assert f.has_kerning and f.kerning(1, 2) == -80 and f.kerning(2, 1) == 35 and f.kerning(3, 4) == -7 and f.kerning(1, 3) == 0
+        _, adv, _ = f.load_glyphs([1, 4, 5], "em")
+        assert adv.tolist() == [0.6, 0.63, 0.25]
+        assert (f.ascender, f.descender, f.line_height, f.underline_position, f.underline_thickness) == (800, -200, 1000, -125, 50)
