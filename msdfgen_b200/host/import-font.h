@@ -5,8 +5,9 @@
 // FreeType, and an atlas build wants thousands of glyphs as ONE flat batch for b200msdf_generate_batch rather than thousands of
 // Shape objects — so the ingest is native here: a TrueType (`glyf`) reader in libmsdfgen_b200_host that walks the outline points
 // exactly as FT_Outline_Decompose does (implied on-curve midpoints with FreeType's integer halving, contours that start on a
-// control point, the closing line; the outline moved so that its origin is where the `hmtx` left side bearing puts it) and applies msdfgen's callbacks' rules (zero-length edges dropped, degenerate quadratics lowered
-// to lines by the EdgeHolder factory, empty contours not kept), straight into flat segment arrays.
+// control point, the closing line; the outline moved so that its origin is where the `hmtx` left side bearing puts it) and applies
+// msdfgen's callbacks' rules (zero-length edges dropped, degenerate quadratics lowered to lines by the EdgeHolder factory, empty
+// contours not kept), straight into flat segment arrays.
 //
 // The functions below keep msdfgen's names and meaning so that a caller of import-font.h compiles unchanged; FreetypeHandle is an
 // empty token.  Covered: TrueType outlines incl. composite glyphs, cmap formats 4 / 6 / 12, hmtx advances, hhea / post metrics,
