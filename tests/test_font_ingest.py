@@ -150,6 +150,23 @@ def test_shape_interface_equals_flat_ingest(font):
                 assert np.allclose(metrics, np.array([1792, 1536, -256, 1792, 0, 0]) * font.scale(name), rtol=0, atol=0)
 
 
+def test_c_port_equals_compiled_reference_on_real_glyphs(font, ref, port):
+    """The GPU leg (tests/test_zz_real_font.py) checks against the C restatement, which is what travels to the GPU box: pin it to
+    the compiled reference on the same real outlines, default error correction included."""
+    from test_devcore import _frame
+    raw, _, _ = font.load_glyphs(np.arange(font.n_glyphs), "em")
+    shapes = prep.prepare(raw)
+    for g in range(0, font.n_glyphs, 11):
+        cb, pts, od, cl, _ = shapes.glyph(g)
+        if len(od) == 0:
+            continue
+        sx, sy, tx, ty = _frame(FlatShapes.single(cb, pts, od, cl), 32, 32)
+        xf = (sx, sy, tx, ty, -2.0 / sx, 2.0 / sx)
+        for name in ("msdf", "mtsdf"):
+            a, b = port.generate(name, cb, pts, od, cl, xf, 32, 32), ref.generate(name, cb, pts, od, cl, xf, 32, 32)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (g, name)
+
+
 # ---- synthetic fonts: the paths the image's font does not exercise ------------------------------------------------------------------
 
 def _against_freetype(data, chars, port, size=120):
