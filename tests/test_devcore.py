@@ -174,9 +174,11 @@ def _texels(xf, w, h, rng, extra=0):
 
 
 def _texel_bits(d, xf):
-    """The float a generate* call with a 4-pixel range writes for raw distance d."""
+    """The float a generate* call with a 4-pixel range writes for raw distance d: DistanceMapping(Range(-2/s, 2/s)) as the
+    reference and the kernels' epilogue evaluate it, float(scale*(d+translate)) with scale = 1/(upper-lower), translate = -lower."""
+    lower, upper = -2.0 / xf[0], 2.0 / xf[0]
     with np.errstate(over="ignore", invalid="ignore"):
-        return (d * (xf[0] / 4.0) + 0.5).astype(np.float32).view(np.uint32)
+        return ((1.0 / (upper - lower)) * (d + -lower)).astype(np.float32).view(np.uint32)
 
 
 def _affine(g, scale, angle, offset):
