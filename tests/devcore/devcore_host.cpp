@@ -9,7 +9,7 @@
 //
 // Build: g++ -O2 -ffp-contract=off -std=c++17 -Itests/devcore/shim -Imsdfgen_b200/csrc (-ffp-contract=off mirrors nvcc -fmad=false;
 // explicit fma() calls are fused on both sides).
-#include "distance_filter.cuh"
+#include "error_correction.cuh"     // (pulls in kernels.cuh, distance_filter.cuh, distance_core.cuh)
 
 #include <vector>
 
@@ -153,9 +153,107 @@ int runFiltered(const Prepared &pr, const GlyphDesc &g, const uint32_t *cbegin, 
     return guardHits;
 }
 
+// msdfErrorCorrection of one glyph's field, texel by texel through the device's classification code with the IN-PLACE sink (the one
+// k3 uses for texels whose candidate slots overflowed): protectCorners as a scatter over the segments' colour corners, protectEdges,
+// then find_errors_texel with both findErrors passes in one walk and the exact shape distance evaluated on the spot, then apply.
+// The flag logic around the calls follows k2_classify (error_correction.cuh) line for line.
+template <int N, bool OVERLAP>
+void runErrorCorrection(const Prepared &pr, const RawShapes &rs, const GlyphDesc &g, int ecMode, int ecDcm, double minDeviationRatio,
+                        double minImproveRatio, float *field, uint8_t *stencil) {
+    const int w = g.w, h = g.h;
+    const bool useBase = ecDcm == 0 || (ecDcm == 1 && ecMode != 3);
+    const bool useShape = ecDcm == 1 || ecDcm == 2;
+    std::vector<int> state((size_t) w*h, 0);
+    if (ecMode == 2)
+        for (unsigned j = 0; j < g.s1-g.s0; ++j) {
+            const int2 c = corner_of(rs, g, j);
+            for (int d = 0; d < 4; ++d) {
+                const int x = c.x+(d&1), y = c.y+(d>>1);
+                if (x >= 0 && y >= 0 && x < w && y < h)
+                    state[(size_t) y*w+x] |= 1;
+            }
+        }
+    std::vector<double> parked(((size_t) pr.nonEmpty+1)*StoreLayout<2>::PER_CONTOUR);
+    EcCtx<N> e;
+    e.f.base = field; e.f.w = w; e.f.h = h; e.f.flip = 0;
+    e.g = &g;
+    e.minImproveRatio = minImproveRatio;
+    e.slots = nullptr; e.slotCount = nullptr; e.slotCap = 0;
+    e.recs = pr.recs.data(); e.nRec = (int) pr.recs.size();
+    e.store.base = parked.data(); e.store.stride = 1; e.store.perContour = StoreLayout<2>::PER_CONTOUR;
+    const EcSpans sp = ec_spans(g, minDeviationRatio);
+    std::vector<uint8_t> flags((size_t) w*h, 0);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const size_t i = (size_t) y*w+x;
+            bool prot = (state[i]&1) != 0;
+            if (ecMode == 2) {
+                if (!prot)
+                    prot = protect_edges_texel<N>(e.f, x, y, sp.hRadius, sp.vRadius, sp.dRadius);
+            } else if (ecMode == 3)
+                prot = true;
+            TexelState k;
+            k.useBase = useBase;
+            k.protBase = prot;
+            k.useShape = useShape;
+            k.protShape = k.protBase || (useBase && ecDcm == 1);
+            k.errBase = k.errShape = k.overflow = false;
+            k.texel = (unsigned) i;
+            k.queue = nullptr; k.queueCount = nullptr; k.tileTexel = 0;
+            guard_flag() = 0;
+            find_errors_texel<N, 1, OVERLAP>(e, k, x, y, sp.hSpan, sp.vSpan, sp.dSpan);
+            int f = 0;
+            if (ecMode == 3 || prot)
+                f |= EC_FLAG_PROTECTED;
+            if (k.errBase || k.errShape)
+                f |= EC_FLAG_ERROR;
+            if (k.protShape && useShape)
+                f |= EC_FLAG_PROTECTED;
+            flags[i] = (uint8_t) f;
+        }
+    // apply: the classification above read the UNCORRECTED field everywhere, as the reference does (findErrors only marks)
+    for (size_t i = 0; i < flags.size(); ++i) {
+        if (flags[i]&EC_FLAG_ERROR) {
+            float *c = field+i*N;
+            const float m = median3f(c[0], c[1], c[2]);
+            c[0] = c[1] = c[2] = m;
+        }
+        if (stencil)
+            stencil[i] = flags[i];
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+/// msdfErrorCorrection (mode 1 INDISCRIMINATE / 2 EDGE_PRIORITY / 3 EDGE_ONLY, distance check 0 / 1 / 2) of field[h][w][channels] in
+/// place, rows in shape orientation, under the transformation xf = (sx, sy, tx, ty, range lower, range upper); stencil[h][w] may
+/// be NULL.  channels 3 or 4.
+int devcore_error_correction(int channels, int overlap, int ecMode, int ecDcm, double minDeviationRatio, double minImproveRatio, int nContours,
+                             const uint32_t *cbegin, const double *points, const uint8_t *orders, const uint8_t *colors, const double *xf, int w,
+                             int h, float *field, uint8_t *stencil) {
+    if (ecMode == 0)
+        return 0;
+    const Prepared pr = prepare(nContours, cbegin, points, orders, colors);
+    RawShapes rs = { points, orders, colors, cbegin, pr.windings.data() };
+    GlyphDesc g = { };
+    g.sx = xf[0]; g.sy = xf[1]; g.tx = xf[2]; g.ty = xf[3];
+    g.dmScale = 1/(xf[5]-xf[4]); g.dmTranslate = -xf[4];
+    g.w = w; g.h = h;
+    g.c0 = 0; g.c1 = (unsigned) nContours;
+    g.s0 = 0; g.s1 = cbegin[nContours];
+    g.nonEmptyContours = pr.nonEmpty;
+    g.recBase = -1;
+    switch (channels*2+(overlap != 0)) {
+        case 6: runErrorCorrection<3, false>(pr, rs, g, ecMode, ecDcm, minDeviationRatio, minImproveRatio, field, stencil); break;
+        case 7: runErrorCorrection<3, true>(pr, rs, g, ecMode, ecDcm, minDeviationRatio, minImproveRatio, field, stencil); break;
+        case 8: runErrorCorrection<4, false>(pr, rs, g, ecMode, ecDcm, minDeviationRatio, minImproveRatio, field, stencil); break;
+        case 9: runErrorCorrection<4, true>(pr, rs, g, ecMode, ecDcm, minDeviationRatio, minImproveRatio, field, stencil); break;
+        default: return -1;
+    }
+    return 0;
+}
 
 /// The filtered path (k1a_filter + k1b_exact; policy 3: the big-shape kernel's single-pass form, 4: the same without the literal
 /// redo of texels that hit the guard band — what k1_big_blocks does today) at nPts points inside the w x h

@@ -14,16 +14,19 @@
 
 #define __device__
 #define __host__
-#define __global__
+#define __global__ static inline     // kernels are only parsed here, never emitted
+#define __launch_bounds__(...)
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
 #define __align__(n) __attribute__((aligned(n)))
-#define __shared__ static
+#define __shared__ thread_local       // block-scope: static storage; `extern __shared__ T x[]` stays a valid declaration
 #define __restrict__
 
 struct double2 { double x, y; };
 struct DevcoreIdx { unsigned x, y, z; };
-static const DevcoreIdx threadIdx = { 0, 0, 0 }, blockIdx = { 0, 0, 0 };
+static const DevcoreIdx threadIdx = { 0, 0, 0 }, blockIdx = { 0, 0, 0 }, blockDim = { 1, 1, 1 }, gridDim = { 1, 1, 1 };
+struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { int2 r = { x, y }; return r; }
 
 // fp32 helpers of the fast foot-point path.  The device versions are approximate (__cosf: absolute error up to 2^-21.4 on
 // [-pi, pi], CUDA C Programming Guide) or plain IEEE (__frcp_rn); their values only seed a double-precision polish.  The stand-in
@@ -36,6 +39,19 @@ static inline float __frcp_rn(float x) { return 1.0f/x; }
 using std::isfinite;
 
 template <typename T> static inline T atomicAdd(T *p, T v) { T old = *p; *p += v; return old; }
+template <typename T> static inline T atomicOr(T *p, T v) { T old = *p; *p |= v; return old; }
+template <typename T> static inline T atomicMax(T *p, T v) { T old = *p; if (v > old) *p = v; return old; }
+// what only the kernels' bodies (parsed, not emitted) mention
+static inline void __syncthreads() { }
+static inline void __syncwarp(unsigned = 0xffffffffu) { }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline int __any_sync(unsigned, int p) { return p; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+template <typename T> static inline T atomicMin(T *p, T v) { T old = *p; if (v < old) *p = v; return old; }
+static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
+static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
+static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t) p; }
 
 // ---- the fp32 filter (distance_filter.cuh) -----------------------------------------------------------------------------------------
 #define B200_HOST_SHIM 1

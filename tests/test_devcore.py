@@ -7,7 +7,10 @@ of it (distance_filter.cuh: k1a_filter's bounds and masks, k1b_exact's walk over
 form) has two warp votes that reduce to the identity for a warp of one lane, and compiles the same way; it is run with the
 stand-in for sqrt.approx biased by twice the instruction's error in either direction, on shapes moved far from the origin, scaled
 by 1e-3 .. 1e3, stretched and rotated.  The GPU tier checks the kernels themselves (tests/test_gpu_parity.py, test_fuzz.py); this
-tier guards the arithmetic they are built from."""
+tier guards the arithmetic they are built from.  The error-correction pass is covered the same way: error_correction.cuh's
+per-texel classification (protectCorners / protectEdges / both findErrors passes with the exact-distance check evaluated in place —
+the sink k3 uses for overflowed texels) runs on the host over the reference's uncorrected fields and must reproduce the
+reference's corrected floats and stencil bytes in all nine mode x distance-check combinations."""
 import ctypes as C
 import os
 import subprocess
@@ -35,7 +38,8 @@ FOLDED_UNGUARDED = 4        # the big-shape kernel as it runs today: texels that
 def devcore():
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, "libdevcore.so")
-    deps = [SRC, os.path.join(SHIM, "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("distance_core.cuh", "distance_filter.cuh", "cr_math.cuh")]
+    deps = [SRC, os.path.join(SHIM, "cuda_runtime.h")] + [os.path.join(CSRC, f) for f in ("distance_core.cuh", "distance_filter.cuh", "cr_math.cuh",
+                                                                                          "kernels.cuh", "error_correction.cuh")]
     if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
         # -ffp-contract=off is the host's -fmad=false; explicit fma() calls stay fused on both sides
         subprocess.run([CXX, "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", f"-I{SHIM}", f"-I{CSRC}",
@@ -351,3 +355,40 @@ def test_random_slivers_and_lattice_soup_known_limit(devcore, ref):
     values_g, different_g = _soup_run(devcore, ref, "grid", seed=7, count=200)
     print(f"[devcore] unguarded cross-edge near-ties: slivers {different_s} of {values_s} values, lattice soup {different_g} of {values_g}")
     assert different_s <= 2e-3 * values_s and different_g <= 2e-4 * values_g
+
+
+# ---- error correction ------------------------------------------------------------------------------------------------------------
+
+def _error_correction(lib, field, g, xf, overlap, mode, dcm):
+    out = np.ascontiguousarray(field, np.float32).copy()
+    h, w, n = out.shape
+    stencil = np.zeros((h, w), np.uint8)
+    x = np.asarray(xf, np.float64)
+    ratio = C.c_double(1.11111111111111111)
+    rc = lib.devcore_error_correction(C.c_int(n), C.c_int(int(overlap)), C.c_int(mode), C.c_int(dcm), ratio, ratio, C.c_int(g.n_contours),
+                                      _p(g.cbegin, C.c_uint32), _p(g.points, C.c_double), _p(g.orders, C.c_uint8), _p(g.colors, C.c_uint8),
+                                      _p(x, C.c_double), C.c_int(w), C.c_int(h), _p(out, C.c_float), _p(stencil, C.c_uint8))
+    assert rc == 0
+    return out, stencil
+
+
+def test_error_correction_classification_on_the_cpu(devcore, ref):
+    from oracle.bindings import Config, EC_DISABLED
+    shapes = _shapes()[:10] + _shapes()[16::4]
+    floats = 0
+    for i, g in enumerate(shapes):
+        w, h = (32, 32) if i % 2 else (24, 30)
+        sx, sy, tx, ty = _frame(g, w, h)
+        xf = (sx, sy, tx, ty, -2.0 / sx, 2.0 / sx)
+        for name in ("msdf", "mtsdf"):
+            for overlap in (True, False):
+                field = ref.generate(name, g.cbegin, g.points, g.orders, g.colors, xf, w, h, Config(overlap=overlap, ec_mode=EC_DISABLED))
+                for mode in (1, 2, 3):
+                    for dcm in (0, 1, 2):
+                        cfg = Config(overlap=overlap, ec_mode=mode, ec_dcm=dcm)
+                        want, want_stencil = ref.error_correction(field, g.cbegin, g.points, g.orders, g.colors, xf, cfg, want_stencil=True)
+                        got, stencil = _error_correction(devcore, field, g, xf, overlap, mode, dcm)
+                        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (i, name, overlap, mode, dcm)
+                        assert np.array_equal(stencil, want_stencil), (i, name, overlap, mode, dcm)
+                        floats += want.size
+    print(f"[devcore] error correction: {floats} floats and their stencils identical over 9 mode x distance-check combinations")

@@ -150,6 +150,27 @@ def test_shape_interface_equals_flat_ingest(font):
                 assert np.allclose(metrics, np.array([1792, 1536, -256, 1792, 0, 0]) * font.scale(name), rtol=0, atol=0)
 
 
+def test_real_glyphs_error_correction_on_the_cpu(font, ref, devcore):
+    """The default error correction (EDGE_PRIORITY, CHECK_DISTANCE_AT_EDGE) of real outlines through the device's classification
+    code on the host: corrected floats and stencil bytes equal the reference's."""
+    from oracle.bindings import Config, EC_DISABLED
+    from test_devcore import _frame, _error_correction
+    raw, _, _ = font.load_glyphs(np.arange(font.n_glyphs), "em")
+    shapes = prep.prepare(raw)
+    for g in range(0, font.n_glyphs, 4):
+        cb, pts, od, cl, _ = shapes.glyph(g)
+        if len(od) == 0:
+            continue
+        s = FlatShapes.single(cb, pts, od, cl)
+        sx, sy, tx, ty = _frame(s, 32, 32)
+        xf = (sx, sy, tx, ty, -2.0 / sx, 2.0 / sx)
+        for name in ("msdf", "mtsdf") if g % 16 == 0 else ("msdf",):
+            field = ref.generate(name, cb, pts, od, cl, xf, 32, 32, Config(ec_mode=EC_DISABLED))
+            want, want_stencil = ref.error_correction(field, cb, pts, od, cl, xf, Config(), want_stencil=True)
+            got, stencil = _error_correction(devcore, field, s, xf, True, 2, 1)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) and np.array_equal(stencil, want_stencil), (g, name)
+
+
 def test_c_port_equals_compiled_reference_on_real_glyphs(font, ref, port):
     """The GPU leg (tests/test_zz_real_font.py) checks against the C restatement, which is what travels to the GPU box: pin it to
     the compiled reference on the same real outlines, default error correction included."""

@@ -3,7 +3,7 @@ then ONE batch through the C ABI (glyphs above 96 segments take the big-shape ke
 default error correction) — against the oracle's generateMSDF of the same prepared shapes, float for float.
 
 (Named to run last: real-font ingest and the twin rule it led to were added after the round's GPU budget was spent; the texel
-arithmetic of exactly these glyphs is verified on the CPU in tests/test_font_ingest.py.)"""
+arithmetic and the error-correction classification of exactly these glyphs are verified on the CPU in tests/test_font_ingest.py.)"""
 import numpy as np
 import pytest
 
