@@ -20,7 +20,6 @@ def simple(contours):
     out = struct.pack(">hhhhh", len(contours), min(xs), min(ys), max(xs), max(ys))
     out += b"".join(struct.pack(">H", e) for e in ends) + struct.pack(">H", 0)
     out += bytes(1 if p[2] else 0 for p in pts)
-    px = py = 0
     for axis in (0, 1):
         prev = 0
         for p in pts:
