@@ -307,19 +307,21 @@ __device__ inline void prepare_record(const RawShapes &rs, const GlyphDesc &g, u
             const d2 vq = ab+tq*br;
             if (dot(vq, vq) <= 1e-8*(dot(ab, ab)+a))
                 flags |= SEG_EXACT_ROOTS;
-            // Twins: the same curve traversed in the opposite direction by another edge of the glyph — abutting outlines that share
-            // an edge, as font editors leave them.  Every texel nearest to that curve is equidistant from the two, with opposite
-            // signs, and the reference's pick between them hangs on the last bit of its closed-form roots (which differ between
-            // the two directions); only the literal solver reproduces it.  (Exact duplicates in the same direction tie
+            // Chord twins: another edge of the glyph runs from this curve's end point back to its start point — the same curve
+            // traversed in the opposite direction (abutting outlines that share an edge, as font editors leave them), or a
+            // two-edge contour (a sliver when the two nearly coincide).  Texels nearest to such a pair are equidistant from
+            // both, or nearly so, with opposite signs, and the reference's pick between them hangs on the last bit of its
+            // closed-form roots; only the literal solver reproduces that.  (Exact duplicates in the same direction tie
             // identically in every solver.)  Glyph-sized shapes only: the search is linear in the shape's segment count.
             if (!(flags&SEG_EXACT_ROOTS) && g.s1-g.s0 <= 16384u) {
                 for (unsigned k = g.s0; k < g.s1; ++k) {
-                    if (rs.orders[k] != 2 || k == cur)
-                        continue;
                     const double *q = rs.points+8*size_t(k);
-                    if (q[0] == P2.x && q[1] == P2.y && q[2] == P1.x && q[3] == P1.y && q[4] == P0.x && q[5] == P0.y) {
-                        flags |= SEG_EXACT_ROOTS;
-                        break;
+                    if (q[0] == P2.x && q[1] == P2.y && k != cur) {
+                        const int ok = rs.orders[k];
+                        if (q[2*ok] == P0.x && q[2*ok+1] == P0.y) {
+                            flags |= SEG_EXACT_ROOTS;
+                            break;
+                        }
                     }
                 }
             }
