@@ -357,6 +357,51 @@ def test_random_slivers_and_lattice_soup(devcore, ref):
     assert different_s <= 2e-5 * values_s and different_g <= 2e-5 * values_g
 
 
+def _cubic_soup(rng, kind):
+    """1-3 closed contours of 2-6 cubic edges.  kind: cusp (control points on the end points, both on one end, swapped, or doubling
+    back along the chord) | collinear (all four points on one line, controls also beyond the ends) | loop (self-intersecting
+    edges) | lattice (integer coordinates)."""
+    rows, orders, cbegin = [], [], [0]
+    for _ in range(rng.integers(1, 4)):
+        n = rng.integers(2, 7)
+        v = rng.integers(-8, 9, size=(n, 2)).astype(float) if kind == "lattice" else rng.normal(size=(n, 2)) * 4
+        for i in range(n):
+            a, b = v[i], v[(i + 1) % n]
+            if kind == "cusp":
+                c1, c2 = [(a, b), (a, a), (b, b), (a + (b - a) * 1.4, a - (b - a) * 0.3), (b, a)][rng.integers(0, 5)]
+            elif kind == "collinear":
+                t = np.sort(rng.uniform(-0.5, 1.5, 2))
+                c1, c2 = a + (b - a) * t[0], a + (b - a) * t[1]
+            elif kind == "loop":
+                normal = np.array([a[1] - b[1], b[0] - a[0]])
+                c1, c2 = b + normal * 1.5, a + normal * 1.5
+            else:
+                c1, c2 = rng.integers(-8, 9, 2).astype(float), rng.integers(-8, 9, 2).astype(float)
+            rows.append(np.concatenate([a, c1, c2, b]))
+            orders.append(3)
+        cbegin.append(len(orders))
+    colors = np.array([(6, 5, 3)[i % 3] for i in range(len(orders))], np.uint8)
+    return FlatShapes.single(np.array(cbegin, np.uint32), np.array(rows), np.array(orders, np.uint8), colors)
+
+
+@pytest.mark.parametrize("kind", ["cusp", "collinear", "loop", "lattice"])
+def test_degenerate_cubics(devcore, ref, kind):
+    """sd_cubic follows the reference's Newton search step for step, so cubic cusps, straight cubics, loops and lattice ties need no
+    special path: every value identical."""
+    rng = np.random.default_rng(5)
+    for it in range(60):
+        g = _cubic_soup(rng, kind)
+        if not np.all(np.ptp(_control_points(g), 0) > 0):
+            continue
+        xf = _frame(g, 24, 24)
+        pts = _texels(xf, 24, 24, rng, extra=100)
+        for mode, overlap in ((1, True), (2, False), (3, True), (4, False)):
+            want = ref.distance(mode, overlap, g.cbegin, g.points, g.orders, g.colors, pts)
+            got, _ = _filtered(devcore, mode, overlap, FAST_GUARDED, it % 3 - 1, g, xf, 24, 24, pts)
+            same = (_texel_bits(got, xf) == _texel_bits(want, xf)) | (np.isnan(got) & np.isnan(want))
+            assert same.all(), (kind, it, mode, overlap, int((~same).sum()))
+
+
 # ---- error correction ------------------------------------------------------------------------------------------------------------
 
 def _error_correction(lib, field, g, xf, overlap, mode, dcm):
